@@ -1,0 +1,264 @@
+// smfft/detail/block_fft.cuh -- the native block FFT: F independent N-point C2C FFTs on one tile
+// of shared memory, R points per thread, register-resident radix-R passes.
+//
+// Replaces, on the hot path, the reference's per-stage schedules:
+//   do_SMFFT_CT_DIT<P>              CT/FFT-GPU-32bit.cu:334-532  (+ reorder_* 54-329)
+//   do_FFT_Stockham_mk6<P>          ST/FFT-GPU-32bit-Stockham.cu:97-240
+//   do_FFT_Stockham_C2C<P,Dir>      RC/FFT-GPU-32bit-Stockham.cu:106-266
+//   do_FFT_Stockham_R2C_C2R<P,Dir>  RC/FFT-GPU-32bit-Stockham.cu:269-344
+//
+// Algorithm (Stockham autosort, mixed radix r_0 .. r_{P-1}, all powers of two, r_p <= R):
+//   thread t of an FFT (T = N/R threads) always READS the R points  x = t + m*T, m = 0..R-1;
+//   a pass of radix r treats them as U = R/r butterflies: butterfly u = "virtual thread"
+//   j = t + u*T, its q-th input is register m = u + q*U;
+//   twiddle  v[u+qU] *= W_{Ns*r}^{(j mod Ns) q}      (Ns = r_0*..*r_{p-1}, nothing for Ns = 1)
+//   DFT_r in registers, natural order out
+//   WRITES   x = (j div Ns)*Ns*r + (j mod Ns) + q*Ns (the autosort step)
+//   The last pass writes x = t + m*T again, i.e. exactly the slots the thread read, so the
+//   transform is in place on the tile and the final pass needs no barrier.
+// Output is the natural-order un-normalised DFT (CT reorder=1, Stockham).
+//
+// fft_reorder = 0 (output = DFT of the bit-reversed input): the only change
+// is the first read.  brev_e(t + m*T) = brev_a(t)*R + brev_b(m), so a thread reads ONE contiguous
+// run of R points (128-bit loads) in bit-reversed register order -- the permutation that costs the
+// reference 16-24 SHFL + 4-8 LDS/STS + 3-5 BAR per thread is register renaming
+// here, fused into the load.  To keep both that read and the first exchange write conflict-free
+// under SW128, thread t acts as virtual thread j(t) = t ^ ((brev3(t&7) << (a-3)) & ~7): within any
+// 8 consecutive lanes both j & 7 and brev_a(j) & 7 take 8 distinct values.
+#pragma once
+#include "layout.cuh"
+#include "radix.cuh"
+#include "twiddle.cuh"
+
+namespace smfft {
+namespace detail {
+
+template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128>
+struct BlockCfg {
+    static constexpr int E = E_;        // log2 N
+    static constexpr int N = 1 << E_;   // FFT length
+    static constexpr int B = B_;        // log2 R
+    static constexpr int R = 1 << B_;   // points per thread
+    static constexpr int A = E_ - B_;   // log2 T
+    static constexpr int T = 1 << A;    // threads per FFT
+    static constexpr int F = F_;        // FFTs per tile (power of two)
+    static constexpr int L = F_ * N;    // points per tile
+    static constexpr int THREADS = F_ * T;
+    static constexpr int DIR = DIR_;          // 0 forward (exp -), 1 inverse (exp +): FFT_Params::fft_direction
+    static constexpr int REORDER = REORDER_;  // FFT_Params::fft_reorder
+    static constexpr int TW = TW_;
+    using Layout = Layout_;
+    static_assert(E_ > B_, "need at least two threads per FFT");
+    static_assert(B_ >= 1 && B_ <= 5, "1..32 points per thread");
+    // pass plan, large radix first: [R, R, .., R, 2^(E mod B)]
+    static constexpr int P = (E + B - 1) / B;
+    static SMFFT_CX int radix_log2(int p) { return p < E / B ? B : E % B; }
+    static SMFFT_CX int ns_log2(int p)
+    {
+        int s = 0;
+        for (int i = 0; i < p; i++) s += radix_log2(i);
+        return s;
+    }
+};
+
+// ---- tile <-> registers ------------------------------------------------------------------------
+
+// v[m] = tile[fbase + t + m*T]  (natural "column" ownership)
+template <class C>
+SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t)
+{
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
+        const int p0 = C::Layout::phys(fbase + t);  // bits 4..6 do not depend on m
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            v[m] = plat::lds64(s + p0 + m * C::T);
+        });
+    } else {
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            v[m] = plat::lds64(s + C::Layout::phys(fbase + t + m * C::T));
+        });
+    }
+}
+
+template <class C>
+SMFFT_DEV void store_natural(const float2 (&v)[C::R], float2* s, int fbase, int t)
+{
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
+        const int p0 = C::Layout::phys(fbase + t);
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            plat::sts64(s + p0 + m * C::T, v[m]);
+        });
+    } else {
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            plat::sts64(s + C::Layout::phys(fbase + t + m * C::T), v[m]);
+        });
+    }
+}
+
+// virtual thread id used by the first pass of the no-reorder transform (see header comment)
+template <class C>
+SMFFT_DEV int noreorder_vid(int t)
+{
+    if constexpr (C::A >= 3) {
+        const int l = t & 7;
+        const int rev3 = ((l & 1) << 2) | (l & 2) | ((l >> 2) & 1);
+        return t ^ ((rev3 << (C::A - 3)) & ~7 & (C::T - 1));
+    } else {
+        return t;
+    }
+}
+
+// v[m] = tile[fbase + brev_e(j + m*T)] = tile[fbase + brev_a(j)*R + brev_b(m)]: one contiguous run
+template <class C>
+SMFFT_DEV void load_rows_brev(float2 (&v)[C::R], const float2* s, int fbase, int j)
+{
+    const int row0 = fbase + (int)(plat::brev32((unsigned)j) >> (32 - C::A)) * C::R;
+    static_for<C::R / 2>([&](auto CI) {
+        constexpr int c = decltype(CI)::value;
+        const float4 q = plat::lds128(s + C::Layout::phys(row0 + 2 * c));
+        v[brev_c(2 * c, C::B)] = make_float2(q.x, q.y);
+        v[brev_c(2 * c + 1, C::B)] = make_float2(q.z, q.w);
+    });
+}
+
+// ---- one register pass (+ the autosort exchange that follows it) ---------------------------------
+
+template <class C, int PIDX>
+SMFFT_DEV void fft_pass_compute(float2 (&v)[C::R], int vt, const float2* __restrict__ tw)
+{
+    constexpr int c = C::radix_log2(PIDX), r = 1 << c, U = C::R / r;
+    constexpr int NS = 1 << C::ns_log2(PIDX);  // product of the radices already applied
+    if constexpr (NS > 1) {
+        constexpr int WN = NS * r;
+        float2 pw[r];
+        make_twiddle_powers<C::DIR, C::TW, WN, r>(pw, vt & (NS - 1), tw);
+        // when NS > T the butterflies of one thread sit in different residue classes mod NS:
+        // (vt + u*T) mod NS = vt + (u mod D)*T, which adds the constant factor W_{D r}^{(u mod D) q}
+        constexpr int D = NS > C::T ? NS / C::T : 1;
+        static_for<U>([&](auto UI) {
+            constexpr int u = decltype(UI)::value;
+            static_for<r>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                if constexpr (q >= 1) {
+                    float2 x = cmul(v[u + q * U], pw[q]);
+                    if constexpr (D > 1) x = mul_wconst<C::DIR, ((u % D) * q) % (D * r), D * r>(x);
+                    v[u + q * U] = x;
+                }
+            });
+        });
+    }
+    static_for<U>([&](auto UI) {
+        constexpr int u = decltype(UI)::value;
+        dft_regs<C::DIR, r, u, U, C::R>(v);
+    });
+}
+
+template <class C, int PIDX>
+SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, int vt)
+{
+    constexpr int c = C::radix_log2(PIDX), r = 1 << c, U = C::R / r;
+    constexpr int LNS = C::ns_log2(PIDX), NS = 1 << LNS;
+    static_for<U>([&](auto UI) {
+        constexpr int u = decltype(UI)::value;
+        const int j = vt + u * C::T;
+        const int xb = fbase + ((j >> LNS) << (LNS + c)) + (j & (NS - 1));
+        if constexpr (NS == 1) {
+            // r contiguous outputs per butterfly: 128-bit stores
+            static_for<r / 2>([&](auto QI) {
+                constexpr int q = 2 * decltype(QI)::value;
+                const float2 lo = v[u + q * U], hi = v[u + (q + 1) * U];
+                plat::sts128(s + C::Layout::phys(xb + q), make_float4(lo.x, lo.y, hi.x, hi.y));
+            });
+        } else if constexpr (NS % 128 == 0) {
+            const int p0 = C::Layout::phys(xb);  // q*NS leaves bits 0..6 alone
+            static_for<r>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                plat::sts64(s + p0 + q * NS, v[u + q * U]);
+            });
+        } else {
+            static_for<r>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                plat::sts64(s + C::Layout::phys(xb + q * NS), v[u + q * U]);
+            });
+        }
+    });
+}
+
+template <class C, int PIDX>
+SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t, const float2* __restrict__ tw)
+{
+    fft_pass_compute<C, PIDX>(v, vt, tw);
+    if constexpr (PIDX + 1 < C::P) {
+        plat::sync_block();  // every thread has finished reading the previous state of the tile
+        fft_pass_scatter<C, PIDX>(v, s, fbase, vt);
+        plat::sync_block();
+        load_natural<C>(v, s, fbase, t);
+        run_passes<C, PIDX + 1>(v, s, fbase, t, t, tw);
+    }
+}
+
+// In-place FFT of all F transforms of the tile.  Contract: the tile is visible to the whole CTA on
+// entry (caller synchronised); on return each thread has written only slots it read in the last
+// pass, so the caller must synchronise before other threads (or the async proxy) read the tile.
+template <class C>
+SMFFT_DEV void block_fft_tile(float2* s, const float2* __restrict__ tw)
+{
+    const int tid = plat::tid();
+    const int t = tid & (C::T - 1);
+    const int fbase = (tid >> C::A) << C::E;
+    float2 v[C::R];
+    int vt = t;
+    if constexpr (C::REORDER) {
+        load_natural<C>(v, s, fbase, t);
+    } else {
+        vt = noreorder_vid<C>(t);
+        load_rows_brev<C>(v, s, fbase, vt);
+    }
+    run_passes<C, 0>(v, s, fbase, vt, t, tw);
+    store_natural<C>(v, s, fbase, t);
+}
+
+// ---- R2C / C2R pair pass (RC/FFT-GPU-32bit-Stockham.cu:269-344) ----------
+// M = C::N complex points hold one real transform of length 2M.  Each FFT has M/2 pairs (k, M-k),
+// k = 1..M/2, spread over its T threads (R/2 pairs per thread), plus bin 0 on thread 0.
+// INVERSE = 0: call after the forward C2C;  INVERSE = 1: call before the inverse C2C.
+template <class C, int INVERSE>
+SMFFT_DEV void r2c_pair_pass_tile(float2* s, const float2* __restrict__ tw)
+{
+    const int tid = plat::tid();
+    const int t = tid & (C::T - 1);
+    const int fbase = (tid >> C::A) << C::E;
+    constexpr int M = C::N;
+    constexpr float hx = INVERSE ? -0.5f : 0.5f, hy = INVERSE ? 0.5f : -0.5f;
+    if (t == 0) {
+        float2* p0 = s + C::Layout::phys(fbase);
+        const float2 Lv = plat::lds64(p0);
+        const float sc = INVERSE ? 0.5f : 1.0f;
+        plat::sts64(p0, make_float2(sc * (Lv.x + Lv.y), sc * (Lv.x - Lv.y)));
+    }
+    static_for<C::R / 2>([&](auto II) {
+        constexpr int i = decltype(II)::value;
+        const int k = t + 1 + i * C::T;
+        float2* pa = s + C::Layout::phys(fbase + k);
+        float2* pb = s + C::Layout::phys(fbase + M - k);
+        const float2 Av = plat::lds64(pa), Bv = plat::lds64(pb);
+        float2 H1, H2, W;
+        H1.x = 0.5f * (Av.x + Bv.x);
+        H1.y = 0.5f * (Av.y - Bv.y);
+        H2.x = hx * (Av.y + Bv.y);
+        H2.y = hy * (Av.x - Bv.x);
+        if constexpr (C::TW == TW_LUT)
+            W = tw_lut<INVERSE, 2 * M>(tw, k);
+        else
+            W = tw_mufu<INVERSE, 2 * M>(k);
+        const float2 WH = cmul(W, H2);
+        plat::sts64(pa, make_float2(H1.x + WH.x, H1.y + WH.y));
+        if (k != M - k) plat::sts64(pb, make_float2(H1.x - WH.x, -H1.y + WH.y));
+    });
+}
+
+}  // namespace detail
+}  // namespace smfft

@@ -1,0 +1,28 @@
+// smfft/detail/layout.cuh -- shared-memory layouts for a tile of float2 points.
+//
+// SW128 is the layout the whole native path lives in: 128-byte rows (16 float2), the 16-byte chunk
+// index inside a row XORed with (row & 7).  It is exactly the TMA hardware SWIZZLE_128B pattern, so
+// cp.async.bulk.tensor produces / consumes it directly, and it makes every access pattern of the
+// FFT passes bank-conflict free at once:
+//   * "column" accesses x = t + m*T by consecutive threads (64-bit): 16 lanes cover one row;
+//   * "row" accesses of 16 contiguous points by consecutive threads (128-bit): 8 lanes hit 8 chunks;
+//   * exchange writes j*r + q (first pass) and (j/Ns)*Ns*r + j%Ns + q*Ns, Ns >= 16 (later passes).
+// The reference pads instead (stride 33 / 132 per warp, CT/FFT-GPU-32bit.cu:142-146, 252-256) and
+// still has 2-way conflicts in reorder_256/512 and the Stockham writes.
+#pragma once
+#include "platform.cuh"
+
+namespace smfft {
+namespace detail {
+
+struct LayoutSW128 {
+    // x: logical float2 index inside the tile (tile base 1024-byte aligned)
+    static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 4) & 7) << 1); }
+};
+
+struct LayoutLinear {
+    static SMFFT_HOST_DEV int phys(int x) { return x; }
+};
+
+}  // namespace detail
+}  // namespace smfft

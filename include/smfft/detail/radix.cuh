@@ -1,0 +1,52 @@
+// smfft/detail/radix.cuh -- register-resident radix-2/4/8/16/32 DFTs.
+//
+// A thread keeps RTOT complex values in registers.  dft_regs<DIR, LEN, OFF, STRIDE>() replaces the
+// LEN values v[OFF + i*STRIDE] (i = 0..LEN-1) by their LEN-point DFT, natural order in and out.
+// The network is a decimation-in-frequency nest with compile-time twiddles; the trailing bit
+// reversal is register renaming (every index is a compile-time constant after unrolling).
+// This replaces the reference's one-radix-2-stage-per-shuffle/per-barrier schedule
+// (CT/FFT-GPU-32bit.cu:363-531, ST/...:97-240) with log2(LEN) stages per register pass.
+#pragma once
+#include "complex.cuh"
+
+namespace smfft {
+namespace detail {
+
+template <int DIR, int LEN, int OFF, int STRIDE, int RTOT>
+SMFFT_DEV void dif_net(float2 (&v)[RTOT])
+{
+    if constexpr (LEN > 1) {
+        constexpr int H = LEN / 2;
+        static_for<H>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const float2 a = v[OFF + i * STRIDE];
+            const float2 b = v[OFF + (i + H) * STRIDE];
+            v[OFF + i * STRIDE] = cadd(a, b);
+            v[OFF + (i + H) * STRIDE] = mul_wconst<DIR, i, LEN>(csub(a, b));
+        });
+        dif_net<DIR, H, OFF, STRIDE, RTOT>(v);
+        dif_net<DIR, H, OFF + H * STRIDE, STRIDE, RTOT>(v);
+    }
+}
+
+template <int DIR, int LEN, int OFF, int STRIDE, int RTOT>
+SMFFT_DEV void dft_regs(float2 (&v)[RTOT])
+{
+    static_assert(OFF + (LEN - 1) * STRIDE < RTOT, "register group out of range");
+    dif_net<DIR, LEN, OFF, STRIDE, RTOT>(v);
+    if constexpr (LEN > 2) {
+        constexpr int LG = ilog2_c(LEN);
+        float2 t[LEN];
+        static_for<LEN>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            t[i] = v[OFF + brev_c(i, LG) * STRIDE];
+        });
+        static_for<LEN>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            v[OFF + i * STRIDE] = t[i];
+        });
+    }
+}
+
+}  // namespace detail
+}  // namespace smfft

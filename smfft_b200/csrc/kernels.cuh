@@ -1,0 +1,167 @@
+// kernels.cuh -- wrapper kernels of the native path: HBM -> shared tile -> block FFT -> HBM.
+//
+// Replaces the reference wrapper kernels
+//   SMFFT_DIT_external / SMFFT_DIT_multiple        CT/FFT-GPU-32bit.cu:534-572
+//   FFT_GPU_external / FFT_GPU_multiple            ST/FFT-GPU-32bit-Stockham.cu:243-278
+//   FFT_GPU_R2C_C2R_external / _multiple           RC/FFT-GPU-32bit-Stockham.cu:349-384
+// One kernel template covers them all: a tile of L = F*N contiguous points (F whole FFTs) is staged
+// into shared memory in the SW128 layout, transformed in place by L/R threads, and written back.
+//   IO_TMA : persistent CTAs, cp.async.bulk.tensor loads (mbarrier-tracked, STAGES buffers so the
+//            load of tile k+1 and the store of tile k-1 overlap the FFT of tile k), TMA stores.
+//   IO_LDG : same tiles staged by the threads with 16-byte LDG/STG (any 16-byte aligned pointer;
+//            also the A/B comparison for the TMA path).
+// REPS > 1 is the FFT_multiple benchmark: the transform is re-applied in place REPS times.
+#pragma once
+#include "smfft/detail/block_fft.cuh"
+#include "smfft/detail/tma.cuh"
+
+namespace smfft {
+namespace kernels {
+
+enum { IO_TMA = 0, IO_LDG = 1 };
+enum { MODE_C2C = 0, MODE_R2C = 1, MODE_C2R = 2 };
+
+struct TileArgs {
+    plat::TensorMap in_map;   // IO_TMA: [rows][32 x f32], box = tile rows, SWIZZLE_128B
+    plat::TensorMap out_map;
+    const float2* gin;        // IO_LDG
+    float2* gout;
+    long long n_tiles;
+    long long n_points;       // valid float2 points in the batch (tail tile of IO_LDG)
+    const float2* tw;         // W_8192^j table (forward sign)
+};
+
+// the per-tile transform; tile visible on entry, caller synchronises after
+template <class C, int MODE, int REPS>
+SMFFT_DEV void tile_transform(float2* s, const float2* __restrict__ tw)
+{
+#pragma unroll 1
+    for (int rep = 0; rep < REPS; rep++) {
+        if constexpr (MODE == MODE_C2C) {
+            detail::block_fft_tile<C>(s, tw);
+        } else if constexpr (MODE == MODE_R2C) {
+            detail::block_fft_tile<C>(s, tw);
+            plat::sync_block();
+            detail::r2c_pair_pass_tile<C, 0>(s, tw);
+        } else {
+            detail::r2c_pair_pass_tile<C, 1>(s, tw);
+            plat::sync_block();
+            detail::block_fft_tile<C>(s, tw);
+        }
+        if (rep + 1 < REPS) plat::sync_block();
+    }
+}
+
+template <class C>
+SMFFT_DEV void coop_load_tile(float2* s, const float2* __restrict__ g, long long valid_points)
+{
+    constexpr int CHUNKS = C::L / 2, PER = CHUNKS / C::THREADS;
+    static_assert(CHUNKS % C::THREADS == 0, "tile chunks must divide evenly over the CTA");
+    const int tid = plat::tid();
+    float4 q[PER];
+    detail::static_for<PER>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const int ch = tid + i * C::THREADS;
+        q[i] = (2LL * ch < valid_points) ? plat::ldg128_stream(g + 2 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
+    detail::static_for<PER>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const int ch = tid + i * C::THREADS;
+        plat::sts128(s + C::Layout::phys(2 * ch), q[i]);
+    });
+}
+
+template <class C>
+SMFFT_DEV void coop_store_tile(const float2* s, float2* __restrict__ g, long long valid_points)
+{
+    constexpr int CHUNKS = C::L / 2, PER = CHUNKS / C::THREADS;
+    const int tid = plat::tid();
+    detail::static_for<PER>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const int ch = tid + i * C::THREADS;
+        const float4 q = plat::lds128(s + C::Layout::phys(2 * ch));
+        if (2LL * ch < valid_points) plat::stg128_stream(g + 2 * ch, q);
+    });
+}
+
+template <class C, int MODE, int IO, int STAGES, int REPS>
+SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
+{
+    constexpr int TILE_BYTES = C::L * 8;
+    constexpr int ROWS = C::L / 16;  // 128-byte rows per tile
+    static_assert(TILE_BYTES % 1024 == 0, "tile must be a multiple of the 1 KB swizzle atom");
+    const int tid = plat::tid();
+    const long long first = plat::bid(), step = plat::nblocks();
+    const long long my_tiles = first < args.n_tiles ? (args.n_tiles - first + step - 1) / step : 0;
+
+    if constexpr (IO == IO_TMA) {
+        uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * TILE_BYTES);
+        auto stage_ptr = [&](long long k) { return reinterpret_cast<float2*>(smem + (int)(k % STAGES) * TILE_BYTES); };
+        auto issue_load = [&](long long k) {
+            uint64_t* bar = &full[k % STAGES];
+            plat::mbar_arrive_expect_tx(bar, TILE_BYTES);
+            plat::tma_load_2d(stage_ptr(k), &args.in_map, 0, (int)((first + k * step) * ROWS), bar);
+        };
+        if (tid == 0) {
+            for (int i = 0; i < STAGES; i++) plat::mbar_init(&full[i], 1);
+            plat::mbar_fence_init();
+            plat::tma_prefetch_desc(&args.in_map);
+            plat::tma_prefetch_desc(&args.out_map);
+        }
+        plat::sync_block();
+        if (tid == 0) {
+            for (long long k = 0; k < STAGES - 1 && k < my_tiles; k++) issue_load(k);
+        }
+        for (long long k = 0; k < my_tiles; k++) {
+            if (tid == 0) {
+                const long long kn = k + STAGES - 1;  // refill the buffer tile k-1 has just left
+                if (kn < my_tiles) {
+                    if (k > 0) plat::bulk_wait_read0();
+                    issue_load(kn);
+                }
+            }
+            plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
+            float2* s = stage_ptr(k);
+            tile_transform<C, MODE, REPS>(s, args.tw);
+            plat::fence_proxy_async();
+            plat::sync_block();
+            if (tid == 0) {
+                plat::tma_store_2d(&args.out_map, 0, (int)((first + k * step) * ROWS), s);
+                plat::bulk_commit();
+            }
+        }
+        if (tid == 0) plat::bulk_wait0();
+    } else {
+        float2* s = reinterpret_cast<float2*>(smem);
+        for (long long k = 0; k < my_tiles; k++) {
+            const long long p0 = (first + k * step) * C::L;
+            const long long valid = args.n_points - p0;
+            coop_load_tile<C>(s, args.gin + p0, valid);
+            plat::sync_block();
+            tile_transform<C, MODE, REPS>(s, args.tw);
+            plat::sync_block();
+            coop_store_tile<C>(s, args.gout + p0, valid);
+            if (k + 1 < my_tiles) plat::sync_block();
+        }
+    }
+}
+
+template <class C, int IO, int STAGES>
+constexpr int smem_bytes()
+{
+    return (IO == IO_TMA ? STAGES * C::L * 8 + 8 * STAGES : C::L * 8) + 1024;  // + alignment slack
+}
+
+#if !defined(SMFFT_EMU)
+template <class C, int MODE, int IO, int STAGES, int REPS, int MINB>
+__global__ void __launch_bounds__(C::THREADS, MINB) smfft_tile_kernel(const __grid_constant__ TileArgs args)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t a = plat::smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (a & 1023u)) & 1023u);  // SW128 needs a 1 KB aligned tile
+    tile_kernel_body<C, MODE, IO, STAGES, REPS>(args, smem);
+}
+#endif
+
+}  // namespace kernels
+}  // namespace smfft

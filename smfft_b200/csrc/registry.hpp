@@ -1,0 +1,84 @@
+// registry.hpp -- table of compiled kernel instances, filled by the per-size translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "tuning.hpp"
+
+namespace smfft {
+namespace host {
+
+struct KernelEntry {
+    int mode, e, dir, reorder, io, tw, reps;  // lookup key (e = log2 of the complex length)
+    int tile_points, threads, smem_bytes, minb, stages;
+    const void* func;
+};
+
+struct EntryList {
+    const KernelEntry* entries;
+    int count;
+};
+
+template <int E, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
+KernelEntry make_entry()
+{
+    using Tn = kernels::Tuning<E>;
+    using C = detail::BlockCfg<E, Tn::B, Tn::F, DIR, REORDER, TW>;
+    constexpr int ST = IO == kernels::IO_TMA ? Tn::STAGES : 1;
+    KernelEntry k;
+    k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
+    k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST>();
+    k.minb = Tn::MINB; k.stages = ST;
+    k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, Tn::MINB>);
+    return k;
+}
+
+// every instance the C ABI can dispatch to for one size
+template <int E>
+EntryList build_entries()
+{
+    using namespace kernels;
+    static KernelEntry tab[64];
+    static int n = 0;
+    if (n == 0) {
+        int i = 0;
+#define SMFFT_ADD(...) tab[i++] = make_entry<E, __VA_ARGS__>()
+        // C2C external (FFT_external_benchmark): dir x reorder x io x twiddle
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_MUFU, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA, TW_MUFU, 1);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_MUFU, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_MUFU, 1);
+        // C2C multiple (FFT_multiple_benchmark, 100 reps in place): compute-bound, LDG staging only
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_LUT, 100);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 100);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_MUFU, 100); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_MUFU, 100);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_MUFU, 100); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_MUFU, 100);
+        // R2C / C2R external (complex core 2^E, real length 2^(E+1))
+        SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA, TW_LUT, 1);
+        SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA, TW_MUFU, 1);
+        SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_LDG, TW_LUT, 1);
+        SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_LDG, TW_MUFU, 1);
+        // R2C multiple (forward only, as RC:445-457)
+        SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_MUFU, 100);
+#undef SMFFT_ADD
+        n = i;
+    }
+    return EntryList{tab, n};
+}
+
+// defined one per translation unit (inst_e5.cu ... inst_e12.cu) so the sizes compile in parallel
+EntryList entries_e5();
+EntryList entries_e6();
+EntryList entries_e7();
+EntryList entries_e8();
+EntryList entries_e9();
+EntryList entries_e10();
+EntryList entries_e11();
+EntryList entries_e12();
+
+}  // namespace host
+}  // namespace smfft

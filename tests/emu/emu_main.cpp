@@ -1,0 +1,261 @@
+// emu_main.cpp -- SIMT-emulator driver: runs the smfft kernel templates on the CPU.  TESTS ONLY.
+// Built by tests/emu/build_emu.py into tests/emu/_build/libsmfft_emu.so and called through ctypes.
+#include "emu_runtime.hpp"
+
+#include "kernels.cuh"
+#include "tuning.hpp"
+
+namespace smfft {
+namespace emu {
+
+Block* g_blk = nullptr;
+
+void run_tma_op(const TmaOp& op)
+{
+    const TensorMapEmu* m = op.map;
+    for (int r = 0; r < m->box_rows; r++) {
+        const long long grow = (long long)op.row0 + r;
+        for (int c = 0; c < 8; c++) {
+            unsigned char* sp = op.smem + (size_t)r * 128 + (size_t)((c ^ (r & 7)) * 16);  // SWIZZLE_128B
+            if (op.kind == 0) {
+                if (grow < m->total_rows)
+                    memcpy(sp, m->base + grow * 128 + c * 16, 16);
+                else
+                    memset(sp, 0, 16);  // out-of-bounds rows are zero-filled
+            } else if (grow < m->total_rows) {
+                memcpy(m->base + grow * 128 + c * 16, sp, 16);  // out-of-bounds rows are clipped
+            }
+        }
+    }
+    if (op.kind == 0) *op.bar ^= 1ull;  // phase complete
+}
+
+void drain_tma(int owner_only, int kind_only)
+{
+    Block* b = g_blk;
+    std::vector<TmaOp> keep;
+    for (const TmaOp& op : b->queue) {
+        if ((owner_only < 0 || op.owner == owner_only) && (kind_only < 0 || op.kind == kind_only))
+            run_tma_op(op);
+        else
+            keep.push_back(op);
+    }
+    b->queue.swap(keep);
+}
+
+static void fiber_entry()
+{
+    Block* b = g_blk;
+    b->body();
+    b->done[b->cur] = 1;
+    b->alive--;
+    if (b->alive > 0 && b->arrived == b->alive) {  // exited threads release a pending barrier
+        b->arrived = 0;
+        b->gen++;
+    }
+    swapcontext(&b->ctx[b->cur], &b->sched);
+}
+
+static void analyse_banks(Block& b, BankStats* st)
+{
+    const int nw = (b.nthreads + 31) / 32;
+    for (int w = 0; w < nw; w++) {
+        const int l0 = w * 32, l1 = std::min(b.nthreads, l0 + 32);
+        const size_t n = b.log[l0].size();
+        bool uniform = true;
+        for (int l = l0; l < l1; l++) uniform &= (b.log[l].size() == n);
+        if (!uniform) continue;  // divergent warp (e.g. the bin-0 lane of the R2C pass): not analysed
+        for (size_t i = 0; i < n; i++) {
+            const int width = b.log[l0][i].width;
+            const int group = width == 8 ? 16 : 8;  // lanes served together
+            long long waves = 0;
+            for (int g0 = l0; g0 < l1; g0 += group) {
+                // per bank: set of distinct 32-bit words requested
+                std::vector<uint32_t> words[32];
+                for (int l = g0; l < std::min(l1, g0 + group); l++) {
+                    const SmemAccess& a = b.log[l][i];
+                    if (a.width != width) { fprintf(stderr, "emu: divergent access width\n"); abort(); }
+                    for (int k = 0; k < width / 4; k++) {
+                        const uint32_t word = a.addr / 4 + k;
+                        auto& v = words[word & 31];
+                        bool seen = false;
+                        for (uint32_t x : v) seen |= (x == word);
+                        if (!seen) v.push_back(word);
+                    }
+                }
+                size_t deg = 1;
+                for (int bk = 0; bk < 32; bk++) deg = std::max(deg, words[bk].size());
+                waves += (long long)deg;
+            }
+            if (width == 8) { st->instr64++; st->wave64 += waves; }
+            else { st->instr128++; st->wave128 += waves; }
+        }
+    }
+}
+
+void launch(int grid, int threads, size_t smem_bytes, const std::function<void(unsigned char*)>& body, BankStats* stats)
+{
+    const size_t STACK = 256 * 1024;
+    for (int bid = 0; bid < grid; bid++) {
+        Block blk;
+        blk.nthreads = threads;
+        blk.bid = bid;
+        blk.nblocks = grid;
+        blk.ctx.resize(threads);
+        blk.stacks.assign(threads, std::vector<unsigned char>(STACK));
+        blk.done.assign(threads, 0);
+        blk.alive = threads;
+        blk.log.resize(threads);
+        blk.record = stats != nullptr && bid == 0;
+        void* raw = nullptr;
+        if (posix_memalign(&raw, 1024, smem_bytes + 1024)) abort();
+        memset(raw, 0xCD, smem_bytes + 1024);
+        blk.smem = (unsigned char*)raw;
+        blk.smem_bytes = smem_bytes;
+        blk.body = [&]() { body(blk.smem); };
+        g_blk = &blk;
+        for (int t = 0; t < threads; t++) {
+            getcontext(&blk.ctx[t]);
+            blk.ctx[t].uc_stack.ss_sp = blk.stacks[t].data();
+            blk.ctx[t].uc_stack.ss_size = STACK;
+            blk.ctx[t].uc_link = &blk.sched;
+            makecontext(&blk.ctx[t], (void (*)())fiber_entry, 0);
+        }
+        long rounds = 0;
+        while (blk.alive > 0) {
+            for (int t = 0; t < threads; t++) {
+                if (blk.done[t]) continue;
+                blk.cur = t;
+                swapcontext(&blk.sched, &blk.ctx[t]);
+            }
+            drain_tma(-1, -1);  // the async proxy makes progress between scheduling rounds
+            if (++rounds > 10000000) { fprintf(stderr, "emu: block %d does not terminate\n", bid); abort(); }
+        }
+        drain_tma(-1, -1);
+        if (blk.record) analyse_banks(blk, stats);
+        free(raw);
+        g_blk = nullptr;
+    }
+}
+
+}  // namespace emu
+}  // namespace smfft
+
+// -------------------------------------------------------------------------------------------------
+using namespace smfft;
+
+static std::vector<float2> g_tw;
+static const float2* twiddle_table()
+{
+    if (g_tw.empty()) {
+        g_tw.resize(kTwiddleTableSize);
+        for (int j = 0; j < kTwiddleTableSize; j++) {
+            const double a = -2.0 * M_PI * (double)j / (double)kTwiddleTableSize;
+            g_tw[j] = make_float2((float)cos(a), (float)sin(a));
+        }
+    }
+    return g_tw.data();
+}
+
+template <int E, int B, int F, int MODE, int DIR, int REORDER, int IO, int TW, int STAGES, int REPS>
+static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, double* bank_factor)
+{
+    using C = detail::BlockCfg<E, B, F, DIR, REORDER, TW>;
+    constexpr int ST = IO == kernels::IO_TMA ? STAGES : 1;
+    kernels::TileArgs args;
+    const long long n_points = n_ffts * C::N;
+    const long long n_tiles = (n_points + C::L - 1) / C::L;
+    args.in_map = emu::TensorMapEmu{(unsigned char*)in, n_points / 16, C::L / 16};
+    args.out_map = emu::TensorMapEmu{(unsigned char*)out, n_points / 16, C::L / 16};
+    args.gin = in;
+    args.gout = out;
+    args.n_tiles = n_tiles;
+    args.n_points = n_points;
+    args.tw = twiddle_table();
+    emu::BankStats st;
+    if (grid <= 0 || grid > n_tiles) grid = (int)n_tiles;
+    emu::launch(grid, C::THREADS, kernels::smem_bytes<C, IO, ST>(),
+                [&](unsigned char* smem) { kernels::tile_kernel_body<C, MODE, IO, ST, REPS>(args, smem); },
+                bank_factor ? &st : nullptr);
+    if (bank_factor) *bank_factor = st.factor();
+    return 0;
+}
+
+// dispatch over (dir, reorder, io, tw) for a fixed shape
+template <int E, int B, int F, int MODE, int STAGES, int REPS>
+static int run_shape(const float2* in, float2* out, long long n_ffts, int dir, int reorder, int io, int tw, int grid,
+                     double* bf)
+{
+#define CASE(D, RO, I, T)                                                     \
+    if (dir == D && reorder == RO && io == I && tw == T)                      \
+        return run_cfg<E, B, F, MODE, D, RO, I, T, STAGES, REPS>(in, out, n_ffts, grid, bf);
+    if constexpr (MODE == kernels::MODE_C2C) {
+        CASE(0, 1, 0, 0) CASE(0, 0, 0, 0) CASE(1, 1, 0, 0) CASE(1, 0, 0, 0)
+        CASE(0, 1, 1, 0) CASE(0, 0, 1, 0) CASE(1, 1, 1, 0) CASE(1, 0, 1, 0)
+        CASE(0, 1, 0, 1) CASE(0, 0, 0, 1) CASE(1, 1, 0, 1) CASE(1, 0, 0, 1)
+        CASE(0, 1, 1, 1) CASE(1, 0, 1, 1)
+    } else if constexpr (MODE == kernels::MODE_R2C) {
+        CASE(0, 1, 0, 0) CASE(0, 1, 1, 0) CASE(0, 1, 0, 1)
+    } else {
+        CASE(1, 1, 0, 0) CASE(1, 1, 1, 0) CASE(1, 1, 0, 1)
+    }
+#undef CASE
+    return -1;
+}
+
+extern "C" {
+
+// product shapes (tuning.hpp): e = log2 complex length
+int emu_run(const void* in, void* out, int e, long long n_ffts, int mode, int dir, int reorder, int io, int tw,
+            int reps, int grid, double* bank_factor)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+#define SHAPE(E)                                                                                                    \
+    if (e == E) {                                                                                                   \
+        using Tn = kernels::Tuning<E>;                                                                              \
+        if (mode == 0 && reps == 1) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 0 && reps == 3) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 3>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 1 && reps == 1) return run_shape<E, Tn::B, Tn::F, 1, Tn::STAGES, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 2 && reps == 1) return run_shape<E, Tn::B, Tn::F, 2, Tn::STAGES, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+    }
+    SHAPE(5) SHAPE(6) SHAPE(7) SHAPE(8) SHAPE(9) SHAPE(10) SHAPE(11) SHAPE(12)
+#undef SHAPE
+    return -1;
+}
+
+// alternative shapes: exercise the generic pass machinery (other radices, tile sizes, stage counts)
+int emu_run_alt(const void* in, void* out, int variant, long long n_ffts, int dir, int reorder, int io, int tw, int grid,
+                double* bank_factor)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+    switch (variant) {
+        case 0: return run_shape<10, 3, 1, 0, 1, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 1024 = 8*8*8*2, R=8
+        case 1: return run_shape<10, 5, 4, 0, 3, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 1024 = 32*32, 3 stages
+        case 2: return run_shape<9, 3, 4, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);    // 512 = 8*8*8
+        case 3: return run_shape<7, 2, 8, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);    // 128, R=4 (compat shape)
+        case 4: return run_shape<12, 4, 2, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 2 x 4096 per tile
+        case 5: return run_shape<6, 3, 16, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 64 = 8*8
+        case 6: return run_shape<5, 2, 16, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 32 = 4*4*2
+        case 7: return run_shape<11, 5, 1, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 2048 = 32*32*2
+    }
+    return -1;
+}
+
+int emu_alt_length(int variant)
+{
+    static const int n[] = {1024, 1024, 512, 128, 4096, 64, 32, 2048};
+    return variant >= 0 && variant < 8 ? n[variant] : -1;
+}
+
+int emu_tile_points(int e)
+{
+    switch (e) {
+#define TP(E) case E: return kernels::Tuning<E>::F << E;
+        TP(5) TP(6) TP(7) TP(8) TP(9) TP(10) TP(11) TP(12)
+#undef TP
+    }
+    return -1;
+}
+}
