@@ -19,18 +19,26 @@ struct EntryList {
     int count;
 };
 
+// one instance with an explicit shape (used by tools/tune.cu to sweep shapes)
+template <int E, int B, int TILE_E, int STAGES, int MINB, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
+KernelEntry make_entry_shape()
+{
+    using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW>;
+    constexpr int ST = IO == kernels::IO_TMA ? STAGES : 1;
+    KernelEntry k;
+    k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
+    k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST>();
+    k.minb = MINB; k.stages = ST;
+    k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB>);
+    return k;
+}
+
+// the product instance: shape from tuning.hpp
 template <int E, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
 KernelEntry make_entry()
 {
     using Tn = kernels::Tuning<E>;
-    using C = detail::BlockCfg<E, Tn::B, Tn::F, DIR, REORDER, TW>;
-    constexpr int ST = IO == kernels::IO_TMA ? Tn::STAGES : 1;
-    KernelEntry k;
-    k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
-    k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST>();
-    k.minb = Tn::MINB; k.stages = ST;
-    k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, Tn::MINB>);
-    return k;
+    return make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS>();
 }
 
 // every instance the C ABI can dispatch to for one size

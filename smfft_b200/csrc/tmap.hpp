@@ -1,0 +1,42 @@
+// tmap.hpp -- host helper: TMA tensor map of a batch seen as rows of 128 bytes, SWIZZLE_128B.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace smfft {
+namespace host {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+inline EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// rows x 128 bytes, box = box_rows x 128 bytes; returns the CUresult (0 = ok), -1 without an encoder
+inline int encode_tile_map(CUtensorMap* m, const void* base, long long rows, int box_rows)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return -1;
+    cuuint64_t gdim[2] = {32, (cuuint64_t)rows};  // 32 x f32 = one 128-byte row
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return (int)enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace host
+}  // namespace smfft

@@ -1,0 +1,143 @@
+"""CPU checks of the *kernel sources themselves*: include/smfft/detail/*.cuh and
+smfft_b200/csrc/kernels.cuh are compiled with g++ -DSMFFT_EMU and executed by the SIMT emulator in
+tests/emu (one fiber per CUDA thread; TMA / mbarrier emulated as an asynchronous queue), then compared
+with the FP64 oracle.  This is test infrastructure: the product has no CPU path.  GPU parity proper
+is tests/test_gpu_parity.py (-m gpu).  Tolerance: relative L2 <= 1e-5 (north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+from tests.emu.build_emu import build
+
+TOL = 1e-5
+C2C, R2C, C2R = 0, 1, 2
+IO_TMA, IO_LDG = 0, 1
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = ctypes.CDLL(build())
+    P, I, LL, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.POINTER(ctypes.c_double)
+    lib.emu_run.argtypes = [P, P, I, LL, I, I, I, I, I, I, I, D]
+    lib.emu_run_alt.argtypes = [P, P, I, LL, I, I, I, I, I, D]
+    return lib
+
+
+def run(lib, x, e, mode, direction, reorder, io, tw, reps=1, grid=2):
+    x = np.ascontiguousarray(x)
+    out = np.zeros_like(x)
+    bank = ctypes.c_double(0)
+    n_ffts = x.size // (1 << e) if x.dtype == np.complex64 else x.size // (2 << e)
+    rc = lib.emu_run(x.ctypes.data, out.ctypes.data, e, n_ffts, mode, direction, reorder, io, tw, reps, grid, ctypes.byref(bank))
+    assert rc == 0, "configuration not instantiated in the emulator"
+    return out, bank.value
+
+
+def batch(lib, e, extra=1):
+    # a whole number of tiles plus a ragged tail, so the partial-tile path (TMA OOB fill / LDG guards) runs
+    return max(3 * lib.emu_tile_points(e) // (1 << e) // 2, 1) + extra
+
+
+@pytest.mark.parametrize("e", range(5, 13))
+@pytest.mark.parametrize("io", [IO_TMA, IO_LDG])
+def test_c2c_all_modes(emu, e, io):
+    n = 1 << e
+    x = O.uniform_c64(batch(emu, e), n)
+    for direction in (0, 1):
+        for reorder in (1, 0):
+            y, bank = run(emu, x, e, C2C, direction, reorder, io, 0)
+            assert O.rel_l2(y, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL
+            if e >= 8:
+                assert bank == pytest.approx(1.0), "shared-memory accesses must be bank-conflict free for N >= 256"
+
+
+@pytest.mark.parametrize("e", range(5, 13))
+def test_c2c_mufu_twiddles(emu, e):
+    n = 1 << e
+    x = O.uniform_c64(batch(emu, e), n)
+    y, _ = run(emu, x, e, C2C, 0, 1, IO_TMA, 1)
+    assert O.rel_l2(y, O.ct_c2c_fp64(x, False, True)) < TOL
+    y, _ = run(emu, x, e, C2C, 1, 0, IO_LDG, 1)
+    assert O.rel_l2(y, O.ct_c2c_fp64(x, True, False)) < TOL
+
+
+@pytest.mark.parametrize("e", range(5, 13))
+def test_permutation_exact_by_one_hot(emu, e):
+    """reorder=0 must equal DFT(x o brev_e) for every input slot: delta_p -> W^{brev(p) k}."""
+    n = 1 << e
+    perm = O.c_reorder_index(n)
+    ps = np.unique(np.concatenate([np.arange(min(n, 48)), np.random.default_rng(e).integers(0, n, 16), [n - 1]]))
+    x = np.zeros((len(ps), n), np.complex64)
+    x[np.arange(len(ps)), ps] = 1
+    y, _ = run(emu, x, e, C2C, 0, 0, IO_TMA, 0)
+    k = np.arange(n)
+    for row, p in enumerate(ps):
+        # the source slot is recovered as an exact integer from the phase ramp
+        slot = int(np.rint((-np.angle(y[row, 1]) * n / (2 * np.pi)))) % n
+        assert slot == perm[p]
+        assert np.allclose(y[row], np.exp(-2j * np.pi * perm[p] * k / n), atol=5e-6)
+    y1, _ = run(emu, x, e, C2C, 0, 1, IO_TMA, 0)
+    for row, p in enumerate(ps):
+        assert int(np.rint((-np.angle(y1[row, 1]) * n / (2 * np.pi)))) % n == p
+
+
+@pytest.mark.parametrize("e", range(5, 13))
+@pytest.mark.parametrize("io", [IO_TMA, IO_LDG])
+def test_r2c_c2r(emu, e, io):
+    n = 2 << e  # real length
+    x = O.uniform_f32(batch(emu, e), n)
+    y, _ = run(emu, x, e, R2C, 0, 1, io, 0)
+    yc = y.view(np.complex64)
+    assert O.rel_l2(yc, O.r2c_packed_fp64(x)) < TOL
+    h = O.uniform_c64(batch(emu, e), n // 2, seed=5)
+    z, _ = run(emu, h, e, C2R, 1, 1, io, 0)
+    assert O.rel_l2(z.view(np.float32), O.c2r_packed_fp64(h)) < TOL
+    # round trip = N/2 * identity
+    back, _ = run(emu, yc, e, C2R, 1, 1, io, 0)
+    assert O.rel_l2(back.view(np.float32) / (n / 2), x) < TOL
+
+
+@pytest.mark.parametrize("e", [5, 8, 10, 12])
+def test_multiple_reps_in_place(emu, e):
+    """FFT_multiple re-applies the transform in place (CT:563-565); with 3 reps: F^3 x."""
+    n = 1 << e
+    x = (O.uniform_c64(batch(emu, e), n) / np.float32(n)).astype(np.complex64)
+    y, _ = run(emu, x, e, C2C, 0, 1, IO_LDG, 0, reps=3)
+    ref = np.fft.fft(np.fft.fft(np.fft.fft(x.astype(np.complex128))))
+    assert O.rel_l2(y, ref) < TOL
+    y0, _ = run(emu, x, e, C2C, 0, 0, IO_LDG, 0, reps=3)
+    ref0 = x.astype(np.complex128)
+    for _ in range(3):
+        ref0 = O.ct_c2c_fp64(ref0, False, False)
+    assert O.rel_l2(y0, ref0) < TOL
+
+
+@pytest.mark.parametrize("variant", range(8))
+def test_generic_pass_machinery_other_shapes(emu, variant):
+    """Other radix plans / tile shapes / stage counts through the same templates (R = 4, 8, 32)."""
+    n = emu.emu_alt_length(variant)
+    x = O.uniform_c64(9, n)
+    for direction, reorder, io in ((0, 1, 0), (1, 0, 0), (0, 0, 1), (1, 1, 1)):
+        out = np.zeros_like(x)
+        rc = emu.emu_run_alt(x.ctypes.data, out.ctypes.data, variant, 9, direction, reorder, io, 0, 2, None)
+        assert rc == 0
+        assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL
+
+
+def test_edge_inputs(emu):
+    e, n = 10, 1024
+    # all-ones -> N * delta_0 ; ramp ; single FFT (one ragged tile) ; zeros
+    ones = np.ones((1, n), np.complex64)
+    y, _ = run(emu, ones, e, C2C, 0, 1, IO_TMA, 0)
+    assert abs(y[0, 0] - n) < 1e-3 and np.max(np.abs(y[0, 1:])) < 1e-3
+    ramp = (np.arange(n, dtype=np.float32) / n).astype(np.complex64)[None, :]
+    y, _ = run(emu, ramp, e, C2C, 1, 1, IO_LDG, 0)
+    assert O.rel_l2(y, O.ct_c2c_fp64(ramp, True, True)) < TOL
+    z, _ = run(emu, np.zeros((2, n), np.complex64), e, C2C, 0, 0, IO_TMA, 0)
+    assert not z.any()
+    # many tiles on one persistent CTA: every pipeline stage is reused several times
+    x = O.uniform_c64(14, n)
+    y, _ = run(emu, x, e, C2C, 0, 1, IO_TMA, 0, grid=1)
+    assert O.rel_l2(y, O.ct_c2c_fp64(x, False, True)) < TOL
