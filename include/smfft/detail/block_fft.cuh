@@ -26,6 +26,8 @@
 // under SW128, thread t acts as virtual thread j(t) = t ^ ((brev3(t&7) << (a-3)) & ~7): within any
 // 8 consecutive lanes both j & 7 and brev_a(j) & 7 take 8 distinct values.
 #pragma once
+#include <type_traits>
+
 #include "layout.cuh"
 #include "radix.cuh"
 #include "twiddle.cuh"
@@ -33,7 +35,11 @@
 namespace smfft {
 namespace detail {
 
-template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128>
+// Layout_  : layout of the tile on entry and exit (SW128 for the TMA kernels, linear for the
+//            reference-compatible device API);  XLayout_: layout used by the exchanges between passes.
+// VEC128_  : allow 16-byte shared accesses (needs a 16-byte aligned tile).
+template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128, class XLayout_ = Layout_,
+          bool VEC128_ = true>
 struct BlockCfg {
     static constexpr int E = E_;        // log2 N
     static constexpr int N = 1 << E_;   // FFT length
@@ -48,6 +54,9 @@ struct BlockCfg {
     static constexpr int REORDER = REORDER_;  // FFT_Params::fft_reorder
     static constexpr int TW = TW_;
     using Layout = Layout_;
+    using XLayout = XLayout_;
+    static constexpr bool VEC128 = VEC128_;
+    static constexpr bool SAME_LAYOUT = std::is_same<Layout_, XLayout_>::value;
     static_assert(E_ > B_, "need at least two threads per FFT");
     static_assert(B_ >= 1 && B_ <= 5, "1..32 points per thread");
     // pass plan, large radix first: [R, R, .., R, 2^(E mod B)]
@@ -59,16 +68,53 @@ struct BlockCfg {
         for (int i = 0; i < p; i++) s += radix_log2(i);
         return s;
     }
+    // compact twiddle table (TW_LUT): pass p > 0 owns Ns_p entries W_{Ns_p r_p}^k at tw_offset(p);
+    // the R2C/C2R pair pass owns N/2 + 1 entries W_{2N}^k after them
+    static SMFFT_CX int tw_offset(int p)
+    {
+        int o = 0;
+        for (int i = 1; i < p; i++) o += 1 << ns_log2(i);
+        return o;
+    }
+    static constexpr int TW_C2C_ENTRIES = tw_offset((E_ + B_ - 1) / B_);
+    static constexpr int TW_R2C_ENTRIES = (1 << E_) / 2 + 1;
 };
+
+// Fill the compact table from the global FP64-rounded table gtw[j] = exp(-2 pi i j / kTwiddleTableSize).
+// WITH_R2C: also the pair-pass twiddles (direction R2C_INVERSE).  Caller synchronises afterwards.
+template <class C, bool WITH_R2C, int R2C_INVERSE>
+SMFFT_DEV void fill_twiddle_table(float2* stw, const float2* __restrict__ gtw, int tid, int nthreads)
+{
+    if constexpr (C::TW == TW_LUT) {
+        static_for<C::P>([&](auto PI) {
+            constexpr int p = decltype(PI)::value;
+            if constexpr (p >= 1) {
+                constexpr int NS = 1 << C::ns_log2(p), WN = NS << C::radix_log2(p);
+                for (int k = tid; k < NS; k += nthreads) {
+                    float2 w = plat::ldg_ro(gtw + k * (kTwiddleTableSize / WN));
+                    if (C::DIR) w.y = -w.y;
+                    stw[C::tw_offset(p) + k] = w;
+                }
+            }
+        });
+        if constexpr (WITH_R2C) {
+            for (int k = tid; k < C::TW_R2C_ENTRIES; k += nthreads) {
+                float2 w = plat::ldg_ro(gtw + k * (kTwiddleTableSize / (2 * C::N)));
+                if (R2C_INVERSE) w.y = -w.y;
+                stw[C::TW_C2C_ENTRIES + k] = w;
+            }
+        }
+    }
+}
 
 // ---- tile <-> registers ------------------------------------------------------------------------
 
 // v[m] = tile[fbase + t + m*T]  (natural "column" ownership)
-template <class C>
+template <class C, class LY = typename C::Layout>
 SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t)
 {
     if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
-        const int p0 = C::Layout::phys(fbase + t);  // bits 4..6 do not depend on m
+        const int p0 = LY::phys(fbase + t);  // bits 4..6 do not depend on m
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
             v[m] = plat::lds64(s + p0 + m * C::T);
@@ -76,16 +122,16 @@ SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t
     } else {
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
-            v[m] = plat::lds64(s + C::Layout::phys(fbase + t + m * C::T));
+            v[m] = plat::lds64(s + LY::phys(fbase + t + m * C::T));
         });
     }
 }
 
-template <class C>
+template <class C, class LY = typename C::Layout>
 SMFFT_DEV void store_natural(const float2 (&v)[C::R], float2* s, int fbase, int t)
 {
     if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
-        const int p0 = C::Layout::phys(fbase + t);
+        const int p0 = LY::phys(fbase + t);
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
             plat::sts64(s + p0 + m * C::T, v[m]);
@@ -93,7 +139,7 @@ SMFFT_DEV void store_natural(const float2 (&v)[C::R], float2* s, int fbase, int 
     } else {
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
-            plat::sts64(s + C::Layout::phys(fbase + t + m * C::T), v[m]);
+            plat::sts64(s + LY::phys(fbase + t + m * C::T), v[m]);
         });
     }
 }
@@ -116,25 +162,32 @@ template <class C>
 SMFFT_DEV void load_rows_brev(float2 (&v)[C::R], const float2* s, int fbase, int j)
 {
     const int row0 = fbase + (int)(plat::brev32((unsigned)j) >> (32 - C::A)) * C::R;
-    static_for<C::R / 2>([&](auto CI) {
-        constexpr int c = decltype(CI)::value;
-        const float4 q = plat::lds128(s + C::Layout::phys(row0 + 2 * c));
-        v[brev_c(2 * c, C::B)] = make_float2(q.x, q.y);
-        v[brev_c(2 * c + 1, C::B)] = make_float2(q.z, q.w);
-    });
+    if constexpr (C::VEC128) {
+        static_for<C::R / 2>([&](auto CI) {
+            constexpr int c = decltype(CI)::value;
+            const float4 q = plat::lds128(s + C::Layout::phys(row0 + 2 * c));
+            v[brev_c(2 * c, C::B)] = make_float2(q.x, q.y);
+            v[brev_c(2 * c + 1, C::B)] = make_float2(q.z, q.w);
+        });
+    } else {
+        static_for<C::R>([&](auto MI) {
+            constexpr int m = decltype(MI)::value;
+            v[brev_c(m, C::B)] = plat::lds64(s + C::Layout::phys(row0 + m));
+        });
+    }
 }
 
 // ---- one register pass (+ the autosort exchange that follows it) ---------------------------------
 
 template <class C, int PIDX>
-SMFFT_DEV void fft_pass_compute(float2 (&v)[C::R], int vt, const float2* __restrict__ tw)
+SMFFT_DEV void fft_pass_compute(float2 (&v)[C::R], int vt, const float2* tw)
 {
     constexpr int c = C::radix_log2(PIDX), r = 1 << c, U = C::R / r;
     constexpr int NS = 1 << C::ns_log2(PIDX);  // product of the radices already applied
     if constexpr (NS > 1) {
         constexpr int WN = NS * r;
         float2 pw[r];
-        make_twiddle_powers<C::DIR, C::TW, WN, r>(pw, vt & (NS - 1), tw);
+        make_twiddle_powers<C::DIR, C::TW, WN, r>(pw, vt & (NS - 1), tw + C::tw_offset(PIDX));
         // when NS > T the butterflies of one thread sit in different residue classes mod NS:
         // (vt + u*T) mod NS = vt + (u mod D)*T, which adds the constant factor W_{D r}^{(u mod D) q}
         constexpr int D = NS > C::T ? NS / C::T : 1;
@@ -165,15 +218,15 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
         constexpr int u = decltype(UI)::value;
         const int j = vt + u * C::T;
         const int xb = fbase + ((j >> LNS) << (LNS + c)) + (j & (NS - 1));
-        if constexpr (NS == 1) {
+        if constexpr (NS == 1 && C::VEC128) {
             // r contiguous outputs per butterfly: 128-bit stores
             static_for<r / 2>([&](auto QI) {
                 constexpr int q = 2 * decltype(QI)::value;
                 const float2 lo = v[u + q * U], hi = v[u + (q + 1) * U];
-                plat::sts128(s + C::Layout::phys(xb + q), make_float4(lo.x, lo.y, hi.x, hi.y));
+                plat::sts128(s + C::XLayout::phys(xb + q), make_float4(lo.x, lo.y, hi.x, hi.y));
             });
         } else if constexpr (NS % 128 == 0) {
-            const int p0 = C::Layout::phys(xb);  // q*NS leaves bits 0..6 alone
+            const int p0 = C::XLayout::phys(xb);  // q*NS leaves bits 0..6 alone
             static_for<r>([&](auto QI) {
                 constexpr int q = decltype(QI)::value;
                 plat::sts64(s + p0 + q * NS, v[u + q * U]);
@@ -181,35 +234,39 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
         } else {
             static_for<r>([&](auto QI) {
                 constexpr int q = decltype(QI)::value;
-                plat::sts64(s + C::Layout::phys(xb + q * NS), v[u + q * U]);
+                plat::sts64(s + C::XLayout::phys(xb + q * NS), v[u + q * U]);
             });
         }
     });
 }
 
-template <class C, int PIDX>
-SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t, const float2* __restrict__ tw)
+struct NoHook {
+    SMFFT_DEV void operator()() const {}
+};
+
+// hook() runs once, right after the first barrier of the transform: at that point every thread of
+// the CTA has finished ALL work of the previous tile, so the previous tile's buffer may be refilled.
+template <class C, int PIDX, class Hook>
+SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t, const float2* tw, Hook&& hook)
 {
     fft_pass_compute<C, PIDX>(v, vt, tw);
     if constexpr (PIDX + 1 < C::P) {
         plat::sync_block();  // every thread has finished reading the previous state of the tile
+        if constexpr (PIDX == 0) hook();
         fft_pass_scatter<C, PIDX>(v, s, fbase, vt);
         plat::sync_block();
-        load_natural<C>(v, s, fbase, t);
-        run_passes<C, PIDX + 1>(v, s, fbase, t, t, tw);
+        load_natural<C, typename C::XLayout>(v, s, fbase, t);
+        run_passes<C, PIDX + 1>(v, s, fbase, t, t, tw, hook);
     }
 }
 
-// In-place FFT of all F transforms of the tile.  Contract: the tile is visible to the whole CTA on
-// entry (caller synchronised); on return each thread has written only slots it read in the last
-// pass, so the caller must synchronise before other threads (or the async proxy) read the tile.
-template <class C>
-SMFFT_DEV void block_fft_tile(float2* s, const float2* __restrict__ tw)
+// load + all passes; the result is left in registers: v[m] = X[t + m*T] of FFT (tid >> A)
+template <class C, class Hook>
+SMFFT_DEV void block_fft_regs(float2 (&v)[C::R], float2* s, const float2* tw, Hook&& hook)
 {
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
-    float2 v[C::R];
     int vt = t;
     if constexpr (C::REORDER) {
         load_natural<C>(v, s, fbase, t);
@@ -217,8 +274,44 @@ SMFFT_DEV void block_fft_tile(float2* s, const float2* __restrict__ tw)
         vt = noreorder_vid<C>(t);
         load_rows_brev<C>(v, s, fbase, vt);
     }
-    run_passes<C, 0>(v, s, fbase, vt, t, tw);
-    store_natural<C>(v, s, fbase, t);
+    run_passes<C, 0>(v, s, fbase, vt, t, tw, hook);
+}
+
+// In-place FFT of all F transforms of the tile.  Contract: the tile is visible to the whole CTA on
+// entry (caller synchronised); on return each thread has written only slots it read in the last
+// pass, so the caller must synchronise before other threads (or the async proxy) read the tile.
+template <class C>
+SMFFT_DEV void block_fft_tile(float2* s, const float2* tw)
+{
+    float2 v[C::R];
+    block_fft_regs<C>(v, s, tw, NoHook{});
+    const int tid = plat::tid();
+    // with distinct entry/exchange layouts the final slots are not the ones this thread just read
+    if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+    store_natural<C>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
+}
+
+// Same transform, result written straight from registers to global memory (coalesced 8-byte
+// stores: consecutive threads own consecutive points).  g = start of this tile in the output.
+template <class C, class Hook>
+SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid,
+                                        Hook&& hook)
+{
+    float2 v[C::R];
+    block_fft_regs<C>(v, s, tw, hook);
+    const int tid = plat::tid();
+    const int x0 = ((tid >> C::A) << C::E) + (tid & (C::T - 1));
+    if (valid >= C::L) {
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            plat::stg64_stream(g + x0 + m * C::T, v[m]);
+        });
+    } else {
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            if (x0 + m * C::T < valid) plat::stg64_stream(g + x0 + m * C::T, v[m]);
+        });
+    }
 }
 
 // ---- R2C / C2R pair pass (RC/FFT-GPU-32bit-Stockham.cu:269-344) ----------
@@ -226,7 +319,7 @@ SMFFT_DEV void block_fft_tile(float2* s, const float2* __restrict__ tw)
 // k = 1..M/2, spread over its T threads (R/2 pairs per thread), plus bin 0 on thread 0.
 // INVERSE = 0: call after the forward C2C;  INVERSE = 1: call before the inverse C2C.
 template <class C, int INVERSE>
-SMFFT_DEV void r2c_pair_pass_tile(float2* s, const float2* __restrict__ tw)
+SMFFT_DEV void r2c_pair_pass_tile(float2* s, const float2* tw)
 {
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
@@ -251,7 +344,7 @@ SMFFT_DEV void r2c_pair_pass_tile(float2* s, const float2* __restrict__ tw)
         H2.x = hx * (Av.y + Bv.y);
         H2.y = hy * (Av.x - Bv.x);
         if constexpr (C::TW == TW_LUT)
-            W = tw_lut<INVERSE, 2 * M>(tw, k);
+            W = plat::lds64(tw + C::TW_C2C_ENTRIES + k);
         else
             W = tw_mufu<INVERSE, 2 * M>(k);
         const float2 WH = cmul(W, H2);

@@ -70,6 +70,31 @@ SMFFT_DEV void tma_store_2d(const TensorMap* m, int c0, int c1, const void* src_
                  "r"(c0), "r"(c1), "r"(smem_u32(src_smem))
                  : "memory");
 }
+// L2 eviction-priority policies for streaming data (every byte of a batch is touched exactly once)
+SMFFT_DEV uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+SMFFT_DEV void tma_load_2d_hint(void* dst_smem, const TensorMap* m, int c0, int c1, uint64_t* bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+SMFFT_DEV void tma_store_2d_hint(const TensorMap* m, int c0, int c1, const void* src_smem, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(smem_u32(src_smem)), "l"(pol)
+                 : "memory");
+}
+SMFFT_DEV void stg64_hint(float2* p, float2 v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
 SMFFT_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's bulk stores have finished READING shared memory (buffers reusable)
 SMFFT_DEV void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

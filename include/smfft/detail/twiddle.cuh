@@ -1,8 +1,10 @@
 // smfft/detail/twiddle.cuh -- run-time twiddles W_n^m = exp(s 2 pi i m / n).
 //
 // Two sources, selected per kernel instance by measurement (north_star item 3):
-//   TW_LUT  : one accurate base twiddle per pass from a global table of W_TBL^j (host-computed in
-//             FP64, L1/L2 resident), higher powers by complex multiplication in registers;
+//   TW_LUT  : one accurate base twiddle per pass from a compact per-kernel table in SHARED memory
+//             (filled once per persistent CTA from the FP64-rounded global table W_TBL^j, direction
+//             already applied), higher powers by complex multiplication in registers.  A lookup is
+//             one conflict-free LDS.64; nothing on the critical path depends on L1/L2 residency;
 //   TW_MUFU : __sincosf per twiddle (what the reference does on every stage,
 //             CT/FFT-GPU-32bit.cu:18-28), argument reduced to [-pi, pi) in integers first.
 #pragma once
@@ -40,12 +42,13 @@ SMFFT_DEV float2 tw_mufu(int m)
     return w;
 }
 
-// pw[q] = W_WN^{k q} for q = 1 .. RAD-1 (pw[0] is not written)
+// pw[q] = W_WN^{k q} for q = 1 .. RAD-1 (pw[0] is not written).
+// TW_LUT: `pass_tbl` is this pass's compact shared-memory table, pass_tbl[k] = W_WN^k.
 template <int DIR, int TW, int WN, int RAD>
-SMFFT_DEV void make_twiddle_powers(float2 (&pw)[RAD], int k, const float2* __restrict__ tbl)
+SMFFT_DEV void make_twiddle_powers(float2 (&pw)[RAD], int k, const float2* pass_tbl)
 {
     if constexpr (TW == TW_LUT) {
-        pw[1] = tw_lut<DIR, WN>(tbl, k);
+        pw[1] = plat::lds64(pass_tbl + k);
         static_for<RAD>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
             if constexpr (q >= 2) {

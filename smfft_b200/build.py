@@ -67,7 +67,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(f"linked {LIB}")
+    _build_compat(force)
     return LIB
+
+
+def _build_compat(force: bool) -> str:
+    """libsmfft_compat.so: the reference's C++ host symbols (include/smfft_compat.hpp) over the C ABI."""
+    src = os.path.join(CSRC, "compat", "compat_host.cpp")
+    out = os.path.join(PKG, "lib", "libsmfft_compat.so")
+    deps = [src, LIB, os.path.join(ROOT, "include", "smfft.h"), os.path.join(ROOT, "include", "smfft_compat.hpp")]
+    if force or _stale(out, deps):
+        cuda = os.path.dirname(os.path.dirname(NVCC))
+        cmd = [HOST_CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", f"-I{os.path.join(ROOT, 'include')}",
+               f"-I{cuda}/include", src, "-o", out, f"-L{os.path.dirname(LIB)}", "-lsmfft", f"-L{cuda}/lib64", "-lcufft", "-lcudart",
+               "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{cuda}/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"compat link failed:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":

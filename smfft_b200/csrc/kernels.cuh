@@ -18,7 +18,7 @@
 namespace smfft {
 namespace kernels {
 
-enum { IO_TMA = 0, IO_LDG = 1 };
+enum { IO_TMA = 0, IO_LDG = 1, IO_TMA_STG = 2 };  // TMA_STG: TMA loads, results stored from registers
 enum { MODE_C2C = 0, MODE_R2C = 1, MODE_C2R = 2 };
 
 struct TileArgs {
@@ -29,11 +29,12 @@ struct TileArgs {
     long long n_tiles;
     long long n_points;       // valid float2 points in the batch (tail tile of IO_LDG)
     const float2* tw;         // W_8192^j table (forward sign)
+    int l2_hint;              // bit 0: TMA loads evict_first, bit 1: TMA stores evict_first
 };
 
 // the per-tile transform; tile visible on entry, caller synchronises after
 template <class C, int MODE, int REPS>
-SMFFT_DEV void tile_transform(float2* s, const float2* __restrict__ tw)
+SMFFT_DEV void tile_transform(float2* s, const float2* tw)
 {
 #pragma unroll 1
     for (int rep = 0; rep < REPS; rep++) {
@@ -49,6 +50,33 @@ SMFFT_DEV void tile_transform(float2* s, const float2* __restrict__ tw)
             detail::block_fft_tile<C>(s, tw);
         }
         if (rep + 1 < REPS) plat::sync_block();
+    }
+}
+
+// same transform with the result stored straight from registers (C2C and C2R only); hook: see
+// detail::run_passes.  REPS == 0 is the staging-only ceiling measurement (tools/tune).
+template <class C, int MODE, int REPS, class Hook>
+SMFFT_DEV void tile_transform_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid,
+                                        Hook&& hook)
+{
+    static_assert(MODE != MODE_R2C, "the R2C pair pass runs in shared memory after the FFT");
+    if constexpr (REPS == 0) {
+        float2 v[C::R];
+        const int tid = plat::tid();
+        const int fbase = (tid >> C::A) << C::E, t = tid & (C::T - 1);
+        detail::load_natural<C>(v, s, fbase, t);
+        plat::sync_block();
+        hook();
+        detail::static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            if (fbase + t + m * C::T < valid) plat::stg64_stream(g + fbase + t + m * C::T, v[m]);
+        });
+    } else {
+        if constexpr (MODE == MODE_C2R) {
+            detail::r2c_pair_pass_tile<C, 1>(s, tw);
+            plat::sync_block();
+        }
+        detail::block_fft_tile_to_global<C>(s, tw, g, valid, hook);
     }
 }
 
@@ -90,55 +118,83 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
     constexpr int TILE_BYTES = C::L * 8;
     constexpr int ROWS = C::L / 16;  // 128-byte rows per tile
     static_assert(TILE_BYTES % 1024 == 0, "tile must be a multiple of the 1 KB swizzle atom");
+    static_assert(STAGES <= 8, "mbarrier block holds 8 barriers");
     const int tid = plat::tid();
     const long long first = plat::bid(), step = plat::nblocks();
     const long long my_tiles = first < args.n_tiles ? (args.n_tiles - first + step - 1) / step : 0;
+    // compact twiddle table, once per (persistent) CTA; made visible by the first barrier below
+    constexpr int NBUF = IO != IO_LDG ? STAGES : 1;
+    float2* stw = reinterpret_cast<float2*>(smem + NBUF * TILE_BYTES + 64);
+    detail::fill_twiddle_table<C, MODE != MODE_C2C, MODE == MODE_C2R>(stw, args.tw, tid, C::THREADS);
 
-    if constexpr (IO == IO_TMA) {
+    if constexpr (IO == IO_TMA || IO == IO_TMA_STG) {
         uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * TILE_BYTES);
+        const uint64_t pol = args.l2_hint ? plat::l2_policy_evict_first() : 0;
         auto stage_ptr = [&](long long k) { return reinterpret_cast<float2*>(smem + (int)(k % STAGES) * TILE_BYTES); };
         auto issue_load = [&](long long k) {
             uint64_t* bar = &full[k % STAGES];
             plat::mbar_arrive_expect_tx(bar, TILE_BYTES);
-            plat::tma_load_2d(stage_ptr(k), &args.in_map, 0, (int)((first + k * step) * ROWS), bar);
+            if (args.l2_hint & 1)
+                plat::tma_load_2d_hint(stage_ptr(k), &args.in_map, 0, (int)((first + k * step) * ROWS), bar, pol);
+            else
+                plat::tma_load_2d(stage_ptr(k), &args.in_map, 0, (int)((first + k * step) * ROWS), bar);
         };
         if (tid == 0) {
             for (int i = 0; i < STAGES; i++) plat::mbar_init(&full[i], 1);
             plat::mbar_fence_init();
             plat::tma_prefetch_desc(&args.in_map);
-            plat::tma_prefetch_desc(&args.out_map);
+            if constexpr (IO == IO_TMA) plat::tma_prefetch_desc(&args.out_map);
         }
         plat::sync_block();
         if (tid == 0) {
             for (long long k = 0; k < STAGES - 1 && k < my_tiles; k++) issue_load(k);
         }
-        for (long long k = 0; k < my_tiles; k++) {
-            if (tid == 0) {
-                const long long kn = k + STAGES - 1;  // refill the buffer tile k-1 has just left
-                if (kn < my_tiles) {
-                    if (k > 0) plat::bulk_wait_read0();
-                    issue_load(kn);
+        if constexpr (IO == IO_TMA) {
+            for (long long k = 0; k < my_tiles; k++) {
+                if (tid == 0) {
+                    const long long kn = k + STAGES - 1;  // refill the buffer tile k-1 has just left
+                    if (kn < my_tiles) {
+                        if (k > 0) plat::bulk_wait_read0();
+                        issue_load(kn);
+                    }
+                }
+                plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
+                float2* s = stage_ptr(k);
+                tile_transform<C, MODE, REPS>(s, stw);
+                plat::fence_proxy_async();
+                plat::sync_block();
+                if (tid == 0) {
+                    if (args.l2_hint & 2)
+                        plat::tma_store_2d_hint(&args.out_map, 0, (int)((first + k * step) * ROWS), s, pol);
+                    else
+                        plat::tma_store_2d(&args.out_map, 0, (int)((first + k * step) * ROWS), s);
+                    plat::bulk_commit();
                 }
             }
-            plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
-            float2* s = stage_ptr(k);
-            tile_transform<C, MODE, REPS>(s, args.tw);
-            plat::fence_proxy_async();
-            plat::sync_block();
-            if (tid == 0) {
-                plat::tma_store_2d(&args.out_map, 0, (int)((first + k * step) * ROWS), s);
-                plat::bulk_commit();
+            if (tid == 0) plat::bulk_wait0();
+        } else {
+            // results leave from registers: a tile buffer is free as soon as every thread has passed
+            // the first barrier of the NEXT tile, which is where the refill is issued (hook)
+            static_assert(IO != IO_TMA_STG || STAGES >= 2, "register-output staging needs two tile buffers");
+            for (long long k = 0; k < my_tiles; k++) {
+                plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
+                const long long p0 = (first + k * step) * C::L;
+                auto refill = [&]() {
+                    const long long kn = k + STAGES - 1;
+                    if (tid == 0 && kn < my_tiles) issue_load(kn);
+                };
+                tile_transform_to_global<C, MODE, REPS>(stage_ptr(k), stw, args.gout + p0, args.n_points - p0, refill);
             }
         }
-        if (tid == 0) plat::bulk_wait0();
     } else {
         float2* s = reinterpret_cast<float2*>(smem);
+        plat::sync_block();
         for (long long k = 0; k < my_tiles; k++) {
             const long long p0 = (first + k * step) * C::L;
             const long long valid = args.n_points - p0;
             coop_load_tile<C>(s, args.gin + p0, valid);
             plat::sync_block();
-            tile_transform<C, MODE, REPS>(s, args.tw);
+            tile_transform<C, MODE, REPS>(s, stw);
             plat::sync_block();
             coop_store_tile<C>(s, args.gout + p0, valid);
             if (k + 1 < my_tiles) plat::sync_block();
@@ -146,10 +202,12 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
     }
 }
 
-template <class C, int IO, int STAGES>
+// [tile buffers][64 B: mbarriers][twiddle table] + 1 KB alignment slack
+template <class C, int IO, int STAGES, int MODE = MODE_C2C>
 constexpr int smem_bytes()
 {
-    return (IO == IO_TMA ? STAGES * C::L * 8 + 8 * STAGES : C::L * 8) + 1024;  // + alignment slack
+    constexpr int tw = C::TW == TW_LUT ? (C::TW_C2C_ENTRIES + (MODE != MODE_C2C ? C::TW_R2C_ENTRIES : 0)) * 8 : 0;
+    return (IO != IO_LDG ? STAGES : 1) * C::L * 8 + 64 + ((tw + 127) & ~127) + 1024;
 }
 
 #if !defined(SMFFT_EMU)

@@ -24,10 +24,10 @@ template <int E, int B, int TILE_E, int STAGES, int MINB, int MODE, int DIR, int
 KernelEntry make_entry_shape()
 {
     using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW>;
-    constexpr int ST = IO == kernels::IO_TMA ? STAGES : 1;
+    constexpr int ST = IO != kernels::IO_LDG ? STAGES : 1;
     KernelEntry k;
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
-    k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST>();
+    k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();
     k.minb = MINB; k.stages = ST;
     k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB>);
     return k;

@@ -25,7 +25,8 @@ inline EncodeTiledFn tensor_map_encoder()
 }
 
 // rows x 128 bytes, box = box_rows x 128 bytes; returns the CUresult (0 = ok), -1 without an encoder
-inline int encode_tile_map(CUtensorMap* m, const void* base, long long rows, int box_rows)
+// promo: 0 none, 1 64 B, 2 128 B, 3 256 B (L2 promotion);  swizzle: true = SWIZZLE_128B (LayoutSW128)
+inline int encode_tile_map(CUtensorMap* m, const void* base, long long rows, int box_rows, int promo = 3, bool swizzle = true)
 {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return -1;
@@ -34,7 +35,10 @@ inline int encode_tile_map(CUtensorMap* m, const void* base, long long rows, int
     cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return (int)enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                               : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                            : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 

@@ -161,7 +161,7 @@ template <int E, int B, int F, int MODE, int DIR, int REORDER, int IO, int TW, i
 static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, double* bank_factor)
 {
     using C = detail::BlockCfg<E, B, F, DIR, REORDER, TW>;
-    constexpr int ST = IO == kernels::IO_TMA ? STAGES : 1;
+    constexpr int ST = IO != kernels::IO_LDG ? STAGES : 1;
     kernels::TileArgs args;
     const long long n_points = n_ffts * C::N;
     const long long n_tiles = (n_points + C::L - 1) / C::L;
@@ -172,9 +172,10 @@ static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, do
     args.n_tiles = n_tiles;
     args.n_points = n_points;
     args.tw = twiddle_table();
+    args.l2_hint = 0;
     emu::BankStats st;
     if (grid <= 0 || grid > n_tiles) grid = (int)n_tiles;
-    emu::launch(grid, C::THREADS, kernels::smem_bytes<C, IO, ST>(),
+    emu::launch(grid, C::THREADS, kernels::smem_bytes<C, IO, ST, MODE>(),
                 [&](unsigned char* smem) { kernels::tile_kernel_body<C, MODE, IO, ST, REPS>(args, smem); },
                 bank_factor ? &st : nullptr);
     if (bank_factor) *bank_factor = st.factor();
@@ -194,16 +195,58 @@ static int run_shape(const float2* in, float2* out, long long n_ffts, int dir, i
         CASE(0, 1, 1, 0) CASE(0, 0, 1, 0) CASE(1, 1, 1, 0) CASE(1, 0, 1, 0)
         CASE(0, 1, 0, 1) CASE(0, 0, 0, 1) CASE(1, 1, 0, 1) CASE(1, 0, 0, 1)
         CASE(0, 1, 1, 1) CASE(1, 0, 1, 1)
+        if constexpr (STAGES >= 2) { CASE(0, 1, 2, 0) CASE(0, 0, 2, 0) CASE(1, 1, 2, 0) CASE(1, 0, 2, 0) CASE(0, 1, 2, 1) }
     } else if constexpr (MODE == kernels::MODE_R2C) {
         CASE(0, 1, 0, 0) CASE(0, 1, 1, 0) CASE(0, 1, 0, 1)
     } else {
         CASE(1, 1, 0, 0) CASE(1, 1, 1, 0) CASE(1, 1, 0, 1)
+        if constexpr (STAGES >= 2) { CASE(1, 1, 2, 0) }
     }
 #undef CASE
     return -1;
 }
 
+// the configuration behind include/smfft/compat.cuh (reference thread contract: 4 points per thread,
+// linear tile, swizzled exchanges, MUFU twiddles, 8-byte shared accesses)
+template <int E, int MODE, int DIR, int REORDER>
+static int run_compat(const float2* in, float2* out, long long n_ffts, double* bank_factor)
+{
+    using C = detail::BlockCfg<E, 2, (E < 7 ? (128 >> E) : 1), DIR, REORDER, TW_MUFU, detail::LayoutLinear, detail::LayoutSW128, false>;
+    kernels::TileArgs args;
+    const long long n_points = n_ffts * C::N;
+    args.gin = in;
+    args.gout = out;
+    args.n_tiles = (n_points + C::L - 1) / C::L;
+    args.n_points = n_points;
+    args.tw = nullptr;
+    args.l2_hint = 0;
+    emu::BankStats st;
+    emu::launch((int)args.n_tiles, C::THREADS, kernels::smem_bytes<C, kernels::IO_LDG, 1, MODE>(),
+                [&](unsigned char* smem) { kernels::tile_kernel_body<C, MODE, kernels::IO_LDG, 1, 1>(args, smem); },
+                bank_factor ? &st : nullptr);
+    if (bank_factor) *bank_factor = st.factor();
+    return 0;
+}
+
 extern "C" {
+
+int emu_run_compat(const void* in, void* out, int e, long long n_ffts, int mode, int dir, int reorder, double* bank_factor)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+#define CC(E)                                                                                      \
+    if (e == E) {                                                                                  \
+        if (mode == 0 && dir == 0 && reorder == 1) return run_compat<E, 0, 0, 1>(i, o, n_ffts, bank_factor); \
+        if (mode == 0 && dir == 0 && reorder == 0) return run_compat<E, 0, 0, 0>(i, o, n_ffts, bank_factor); \
+        if (mode == 0 && dir == 1 && reorder == 1) return run_compat<E, 0, 1, 1>(i, o, n_ffts, bank_factor); \
+        if (mode == 0 && dir == 1 && reorder == 0) return run_compat<E, 0, 1, 0>(i, o, n_ffts, bank_factor); \
+        if (mode == 1) return run_compat<E, 1, 0, 1>(i, o, n_ffts, bank_factor);                     \
+        if (mode == 2) return run_compat<E, 2, 1, 1>(i, o, n_ffts, bank_factor);                     \
+    }
+    CC(5) CC(6) CC(7) CC(8) CC(9) CC(10) CC(11) CC(12)
+#undef CC
+    return -1;
+}
 
 // product shapes (tuning.hpp): e = log2 complex length
 int emu_run(const void* in, void* out, int e, long long n_ffts, int mode, int dir, int reorder, int io, int tw,

@@ -162,6 +162,10 @@ inline void tma_store_2d(const TensorMap* m, int, int c1, const void* src)
 {
     emu::g_blk->queue.push_back(emu::TmaOp{1, (unsigned char*)src, m, c1, nullptr, tid()});
 }
+inline uint64_t l2_policy_evict_first() { return 0; }
+inline void tma_load_2d_hint(void* dst, const TensorMap* m, int c0, int c1, uint64_t* bar, uint64_t) { tma_load_2d(dst, m, c0, c1, bar); }
+inline void tma_store_2d_hint(const TensorMap* m, int c0, int c1, const void* src, uint64_t) { tma_store_2d(m, c0, c1, src); }
+inline void stg64_hint(float2* p, float2 v, uint64_t) { *p = v; }
 inline void bulk_commit() {}
 inline void bulk_wait_read0() { emu::drain_tma(tid(), 1); }
 inline void bulk_wait0() { emu::drain_tma(tid(), 1); }

@@ -16,21 +16,27 @@ C2C, R2C, C2R = 0, 1, 2
 IO_TMA, IO_LDG = 0, 1
 
 
+IO_TMA_STG = 2
+
+
 @pytest.fixture(scope="module")
 def emu():
     lib = ctypes.CDLL(build())
     P, I, LL, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.POINTER(ctypes.c_double)
     lib.emu_run.argtypes = [P, P, I, LL, I, I, I, I, I, I, I, D]
     lib.emu_run_alt.argtypes = [P, P, I, LL, I, I, I, I, I, D]
+    lib.emu_run_compat.argtypes = [P, P, I, LL, I, I, I, D]
     return lib
 
 
-def run(lib, x, e, mode, direction, reorder, io, tw, reps=1, grid=2):
+def run(lib, x, e, mode, direction, reorder, io, tw, reps=1, grid=2, allow_missing=False):
     x = np.ascontiguousarray(x)
     out = np.zeros_like(x)
     bank = ctypes.c_double(0)
     n_ffts = x.size // (1 << e) if x.dtype == np.complex64 else x.size // (2 << e)
     rc = lib.emu_run(x.ctypes.data, out.ctypes.data, e, n_ffts, mode, direction, reorder, io, tw, reps, grid, ctypes.byref(bank))
+    if rc != 0 and allow_missing:
+        return None, None
     assert rc == 0, "configuration not instantiated in the emulator"
     return out, bank.value
 
@@ -141,3 +147,42 @@ def test_edge_inputs(emu):
     x = O.uniform_c64(14, n)
     y, _ = run(emu, x, e, C2C, 0, 1, IO_TMA, 0, grid=1)
     assert O.rel_l2(y, O.ct_c2c_fp64(x, False, True)) < TOL
+
+
+@pytest.mark.parametrize("e", range(5, 13))
+def test_tma_in_register_out_staging(emu, e):
+    """IO_TMA_STG: TMA loads, results stored from registers, refill issued after the first barrier of
+    the next tile.  grid=1 makes one persistent CTA walk many tiles so every buffer is reused."""
+    n = 1 << e
+    x = O.uniform_c64(batch(emu, e, extra=3), n)
+    ran = 0
+    for direction, reorder in ((0, 1), (0, 0), (1, 1), (1, 0)):
+        y, _ = run(emu, x, e, C2C, direction, reorder, IO_TMA_STG, 0, grid=1, allow_missing=True)
+        if y is None:
+            continue  # shapes with a single tile buffer have no register-output variant
+        ran += 1
+        assert O.rel_l2(y, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL
+    h = O.uniform_c64(batch(emu, e), n, seed=5)
+    z, _ = run(emu, h, e, C2R, 1, 1, IO_TMA_STG, 0, allow_missing=True)
+    if z is not None:
+        assert O.rel_l2(z.view(np.float32), O.c2r_packed_fp64(h)) < TOL
+
+
+@pytest.mark.parametrize("e", range(5, 13))
+def test_reference_device_api_configuration(emu, e):
+    """The configuration behind include/smfft/compat.cuh (do_SMFFT_CT_DIT & co.): 4 points per thread,
+    fft_length/4 threads, linear tile in and out, fft_length/N transforms per tile, MUFU twiddles."""
+    n = 1 << e
+    x = O.uniform_c64(8, n)
+    for direction, reorder in ((0, 1), (0, 0), (1, 1), (1, 0)):
+        out = np.zeros_like(x)
+        assert emu.emu_run_compat(x.ctypes.data, out.ctypes.data, e, 8, 0, direction, reorder, None) == 0
+        assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL
+    xr = O.uniform_f32(8, 2 * n)
+    out = np.zeros((8, n), np.complex64)
+    assert emu.emu_run_compat(xr.ctypes.data, out.ctypes.data, e, 8, 1, 0, 1, None) == 0
+    assert O.rel_l2(out, O.r2c_packed_fp64(xr)) < TOL
+    h = O.uniform_c64(8, n, seed=3)
+    out = np.zeros_like(h)
+    assert emu.emu_run_compat(h.ctypes.data, out.ctypes.data, e, 8, 2, 1, 1, None) == 0
+    assert O.rel_l2(out.view(np.float32), O.c2r_packed_fp64(h)) < TOL

@@ -244,3 +244,93 @@ def test_full_size_properties_4GiB(sm):
         torch.cuda.synchronize()
         xs = c64(x.view(nf, n, 2)[nf - 8:])
         assert O.rel_l2(c64(z.view(nf, n, 2)[nf - 8:]), O.ct_c2c_fp64(xs, False, False)) < TOL
+
+
+# ---- the reference's device API (include/smfft/compat.cuh) used from a "user program" ------------------
+
+@pytest.fixture(scope="module")
+def compat():
+    import ctypes
+
+    from tests.compat.build_compat import build
+
+    lib = ctypes.CDLL(build())
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.compat_ct_external.argtypes = [P, P, I, I, I, I]
+    lib.compat_ct_multiple.argtypes = [P, P, I, I, I, I]
+    lib.compat_stockham_external.argtypes = [P, P, I, I]
+    lib.compat_r2c_c2r_external.argtypes = [P, P, I, I, I]
+    lib.compat_user_convolve_1024.argtypes = [P, P, P, I]
+    return lib
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_compat_wrapper_kernels_by_reference_names(compat, n):
+    """SMFFT_DIT_external<FFT_N_{forward,inverse}[_noreorder]> launched with the reference's grid/block."""
+    nf = 64
+    x = O.uniform_c64(nf, n, seed=n + 1)
+    dx = to_dev(x)
+    for inverse in (0, 1):
+        for reorder in (1, 0):
+            dy = torch.zeros_like(dx)
+            assert compat.compat_ct_external(dx.data_ptr(), dy.data_ptr(), n, nf, inverse, reorder) == 0
+            torch.cuda.synchronize()
+            assert O.rel_l2(c64(dy), O.ct_c2c_fp64(x, bool(inverse), bool(reorder))) < TOL
+            assert O.rel_l2(c64(dy), O.c_ct_c2c(x, bool(inverse), bool(reorder))) < TOL
+    big = torch.rand((200 * n, 2), device="cuda")
+    out = torch.empty_like(big)
+    assert compat.compat_ct_multiple(big.data_ptr(), out.data_ptr(), n, 400 if n > 64 else 800, 0, 1) == 0
+    torch.cuda.synchronize()
+
+
+def test_compat_stockham_and_r2c_c2r(compat):
+    for n in (256, 512, 1024, 2048, 4096):
+        x = O.uniform_c64(32, n, seed=n)
+        dx = to_dev(x)
+        dy = torch.zeros_like(dx)
+        assert compat.compat_stockham_external(dx.data_ptr(), dy.data_ptr(), n, 32) == 0
+        torch.cuda.synchronize()
+        assert O.rel_l2(c64(dy), O.stockham_c2c_fp64(x, True)) < TOL           # mk6 is inverse-only
+    for n in (256, 512, 1024, 2048, 4096):
+        xr = O.uniform_f32(32, n, seed=n)
+        dx = to_dev(xr)
+        dy = torch.zeros((32, n // 2, 2), dtype=torch.float32, device="cuda")
+        assert compat.compat_r2c_c2r_external(dx.data_ptr(), dy.data_ptr(), n, 32, 0) == 0
+        back = torch.zeros_like(dx)
+        assert compat.compat_r2c_c2r_external(dy.data_ptr(), back.data_ptr(), n, 32, 1) == 0
+        torch.cuda.synchronize()
+        assert O.rel_l2(c64(dy), O.r2c_packed_fp64(xr)) < TOL
+        assert O.rel_l2(back.cpu().numpy() / (n / 2), xr) < TOL
+
+
+def test_compat_device_function_inside_a_user_kernel(compat):
+    """load -> do_SMFFT_CT_DIT<forward> -> pointwise filter -> do_SMFFT_CT_DIT<inverse> -> store in ONE
+    launch: the use case SMFFT exists for (README.md:2, 10-14)."""
+    n, nf = 1024, 48
+    x = O.uniform_c64(nf, n, seed=9)
+    rng = np.random.default_rng(4)
+    h = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    dx, dh = to_dev(x), to_dev(h)
+    dy = torch.zeros_like(dx)
+    assert compat.compat_user_convolve_1024(dx.data_ptr(), dh.data_ptr(), dy.data_ptr(), nf) == 0
+    torch.cuda.synchronize()
+    want = np.fft.ifft(np.fft.fft(x.astype(np.complex128), axis=-1) * h.astype(np.complex128), axis=-1)
+    assert O.rel_l2(c64(dy), want) < TOL
+
+
+@pytest.mark.parametrize("prog,args", [("ct", "1024 2000 2 0 1"), ("ct", "32 1001 1 1 1"), ("ct", "4096 300 1 0 1"),
+                                       ("st", "2048 500 2"), ("rc", "4096 400 2"), ("rc", "512 1000 1")])
+def test_reference_host_programs_run_unmodified(prog, args):
+    """The reference's own FFT.c (unmodified, built by oracle/Makefile `refmain`) linked against
+    libsmfft_compat.so: its self-check against cuFFT must print PASSED (CT/FFT.c:154-160)."""
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", f"FFT_{prog}.exe")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/FFT_*.exe not built")
+    r = subprocess.run([exe] + args.split(), capture_output=True, text=True, timeout=300)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out
+    assert "FAILED" not in out and "Error" not in out, out
+    if prog != "st":  # the Stockham program only self-checks when built with TESTING (ST/debug.h:3, ST/FFT.c:138-144)
+        assert "PASSED" in out, out

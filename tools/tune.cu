@@ -70,7 +70,7 @@ int main(int argc, char** argv)
     fprintf(stderr, "device %s, %d SMs, batch 2^%d points\n", prop.name, sms, lg);
     float2 *in, *out, *tw;
     CK(cudaMalloc(&in, pts * 8));
-    CK(cudaMalloc(&out, pts * 8));
+    CK(cudaMalloc(&out, pts * 8 + (2 << 20)));
     fill_kernel<<<sms * 8, 256>>>((float*)in, (size_t)pts * 2, 20260101u);
     std::vector<float2> h(kTwiddleTableSize);
     for (int j = 0; j < kTwiddleTableSize; j++) {
@@ -84,7 +84,7 @@ int main(int argc, char** argv)
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
 
-    printf("kind,e,n,b,tile_e,stages,minb,io,tw,reorder,threads,smem,ctas_per_sm,regs,ms_med,ms_min,gbps_med,frac_of_copy,check_rel_l2\n");
+    printf("kind,e,n,b,tile_e,stages,minb,io,tw,reorder,reps,hint,out_off,promo,swz,threads,smem,ctas_per_sm,regs,ms_med,ms_min,gbps_med,frac_of_copy,check_rel_l2\n");
     // roofline reference: device copy of the same batch
     double copy_ms = 1e9;
     {
@@ -100,7 +100,7 @@ int main(int argc, char** argv)
         }
         std::sort(t.begin(), t.end());
         copy_ms = t[t.size() / 2];
-        printf("copy_kernel,0,0,0,0,0,0,ldg128,,,512,0,16,0,%.4f,%.4f,%.1f,1.000,\n", copy_ms, t[0], pts * 16.0 / copy_ms / 1e6);
+        printf("copy_kernel,0,0,0,0,0,0,ldg128,,,,,,,,512,0,16,0,%.4f,%.4f,%.1f,1.000,\n", copy_ms, t[0], pts * 16.0 / copy_ms / 1e6);
         t.clear();
         for (int r = 0; r < reps + 2; r++) {
             CK(cudaEventRecord(e0));
@@ -112,11 +112,11 @@ int main(int argc, char** argv)
             if (r >= 2) t.push_back(ms);
         }
         std::sort(t.begin(), t.end());
-        printf("cudaMemcpyD2D,0,0,0,0,0,0,ce,,,0,0,0,0,%.4f,%.4f,%.1f,%.3f,\n", t[t.size() / 2], t[0], pts * 16.0 / t[t.size() / 2] / 1e6, copy_ms / t[t.size() / 2]);
+        printf("cudaMemcpyD2D,0,0,0,0,0,0,ce,,,,,,,,0,0,0,0,%.4f,%.4f,%.1f,%.3f,\n", t[t.size() / 2], t[0], pts * 16.0 / t[t.size() / 2] / 1e6, copy_ms / t[t.size() / 2]);
     }
     add_all_sizes();
     const size_t CHK = 1 << 18;  // points compared between variants
-    std::vector<float2> ref[16][2], got(CHK);
+    std::vector<float2> ref[16][3], got(CHK);
     for (const Variant& v : g_variants) {
         const KernelEntry& k = v.k;
         if (only_e && k.e != only_e) continue;
@@ -127,15 +127,19 @@ int main(int argc, char** argv)
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.func, k.threads, k.smem_bytes));
         if (per_sm < 1) continue;
+        if (v.per_sm > per_sm) continue;  // shape cannot hold that many CTAs per SM
+        if (v.per_sm > 0) per_sm = v.per_sm;
         TileArgs args;
         memset(&args, 0, sizeof(args));
         args.n_points = pts;
         args.n_tiles = pts / k.tile_points;
+        float2* outp = (float2*)((char*)out + v.out_off);
         args.gin = in;
-        args.gout = out;
+        args.gout = outp;
         args.tw = tw;
-        if (k.io == IO_TMA) {
-            if (encode_tile_map(&args.in_map, in, pts / 16, k.tile_points / 16) || encode_tile_map(&args.out_map, out, pts / 16, k.tile_points / 16)) {
+        args.l2_hint = v.hint;
+        if (k.io != IO_LDG) {
+            if (encode_tile_map(&args.in_map, in, pts / 16, k.tile_points / 16, v.promo, v.swz) || encode_tile_map(&args.out_map, outp, pts / 16, k.tile_points / 16, v.promo, v.swz)) {
                 fprintf(stderr, "tensor map encode failed\n");
                 continue;
             }
@@ -143,7 +147,7 @@ int main(int argc, char** argv)
         long long grid = std::min<long long>((long long)sms * per_sm, args.n_tiles);
         void* params[] = {&args};
         std::vector<float> t;
-        CK(cudaMemsetAsync(out, 0, CHK * 8));
+        CK(cudaMemsetAsync(outp, 0, CHK * 8));
         bool ok = true;
         for (int r = 0; r < reps + 2 && ok; r++) {
             CK(cudaEventRecord(e0));
@@ -161,9 +165,13 @@ int main(int argc, char** argv)
         }
         if (!ok) return 3;  // a failed launch poisons the context: stop
         std::sort(t.begin(), t.end());
-        CK(cudaMemcpy(got.data(), out, CHK * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(got.data(), outp, CHK * 8, cudaMemcpyDeviceToHost));
         double rel = 0;
-        auto& rf = ref[k.e][k.reorder];
+        auto& rf = ref[k.e][k.reps == 0 ? 2 : k.reorder];
+        if (k.reps == 0 && rf.empty()) {  // staging-only variants must reproduce the input
+            rf.resize(CHK);
+            CK(cudaMemcpy(rf.data(), in, CHK * 8, cudaMemcpyDeviceToHost));
+        }
         if (rf.empty()) {
             rf = got;
         } else {
@@ -176,8 +184,9 @@ int main(int argc, char** argv)
             rel = sqrt(num / den);
         }
         const double med = t[t.size() / 2];
-        printf("fft,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.e, 1 << k.e, v.b, v.tile_e, k.stages, k.minb,
-               k.io == IO_TMA ? "tma" : "ldg", k.tw == TW_LUT ? "lut" : "mufu", k.reorder, k.threads, k.smem_bytes, per_sm, fa.numRegs, med,
+        printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : "fft", k.e, 1 << k.e, v.b, v.tile_e,
+               k.stages, k.minb, k.io == IO_TMA ? "tma" : (k.io == IO_LDG ? "ldg" : "tma_stg"), k.tw == TW_LUT ? "lut" : "mufu", k.reorder, k.reps, v.hint,
+               v.out_off, v.promo, v.swz, k.threads, k.smem_bytes, per_sm, fa.numRegs, med,
                t[0], pts * 16.0 / med / 1e6, copy_ms / med, rel);
         fflush(stdout);
     }
