@@ -11,8 +11,8 @@
  * signatures so the reference's FFT.c objects link unmodified.
  *
  * Conventions (kept from the reference unless noted):
- *   - plain pointers and sizes only; device pointers are borrowed, out of place, 16-byte aligned
- *     (8-byte aligned pointers are accepted and take a slower staging path);
+ *   - plain pointers and sizes only; device pointers are borrowed, out of place and must be
+ *     16-byte aligned (cudaMalloc returns 256-byte alignment; anything else is rejected);
  *   - all transforms are un-normalised in both directions; C2R returns (N/2) * irfft;
  *   - `*ms` is ACCUMULATED (+=) with the elapsed milliseconds of the one launch, as in
  *     CT:662 / ST:343 / RC:431; the caller zeroes it;
@@ -90,7 +90,8 @@ int smfft_pipeline_host(const void* h_in, void* h_out, int fft_size, long long n
                         int mode, long long chunk_ffts, double* ms);
 
 /* ---- knobs -------------------------------------------------------------------------------------
- * keys: "io" (0 = TMA tensor copies [default], 1 = LDG/STG staging), "twiddle" (0 = table+powers
+ * keys: "io" (0 = measured best TMA staging per size [default], 1 = LDG/STG staging by the threads,
+ * 2 = TMA loads + TMA stores, 3 = TMA loads + stores from registers), "twiddle" (0 = table+powers
  * [default], 1 = MUFU __sincosf), "quirk_4096" (1 = reproduce FFT_4096_inverse_noreorder running
  * the forward transform, CT/SM_FFT_parameters.cuh:388; default 0 = mathematically correct),
  * "ctas_per_sm" (0 = built-in), "device_sms" (read-only). */

@@ -131,14 +131,14 @@ __device__ __forceinline__ void do_SMFFT_CT_DIT(float2* s_input)
 {
     using C = smfft::compat::Cfg<const_params::fft_exp, (const_params::fft_length >> const_params::fft_exp),
                                  const_params::fft_direction, const_params::fft_reorder>;
-    smfft::detail::block_fft_tile<C>(s_input, nullptr);
+    smfft::detail::block_fft_tile<C, smfft::detail::XF_C2C>(s_input, nullptr);
 }
 
 template <class const_params, class const_direction>
 __device__ __forceinline__ void do_FFT_Stockham_C2C(float2* s_input)
 {
     using C = smfft::compat::Cfg<const_params::fft_exp, 1, const_direction::fft_direction, 1>;
-    smfft::detail::block_fft_tile<C>(s_input, nullptr);
+    smfft::detail::block_fft_tile<C, smfft::detail::XF_C2C>(s_input, nullptr);
     __syncthreads();
 }
 
@@ -155,14 +155,14 @@ __device__ __forceinline__ void do_FFT_Stockham_R2C_C2R(float2* s_input)
 {
     using C = smfft::compat::Cfg<const_params::fft_exp, 1, const_direction::fft_direction, 1>;
     if (const_direction::fft_direction == 0) {
-        smfft::detail::block_fft_tile<C>(s_input, nullptr);
+        smfft::detail::block_fft_tile<C, smfft::detail::XF_C2C>(s_input, nullptr);
         __syncthreads();
         smfft::detail::r2c_pair_pass_tile<C, 0>(s_input, nullptr);
         __syncthreads();
     } else {
         smfft::detail::r2c_pair_pass_tile<C, 1>(s_input, nullptr);
         __syncthreads();
-        smfft::detail::block_fft_tile<C>(s_input, nullptr);
+        smfft::detail::block_fft_tile<C, smfft::detail::XF_C2C>(s_input, nullptr);
         __syncthreads();
     }
 }
@@ -195,7 +195,7 @@ __device__ __forceinline__ void tile_out(const float2* s, float2* __restrict__ g
 }  // namespace smfft
 
 template <class const_params>
-__global__ void SMFFT_DIT_external(float2* d_input, float2* d_output)
+__global__ void __launch_bounds__(const_params::fft_length / 4) SMFFT_DIT_external(float2* d_input, float2* d_output)
 {
     __shared__ float2 s_input[const_params::fft_sm_required];
     smfft::compat::tile_in<const_params::fft_length>(s_input, d_input);
@@ -206,7 +206,7 @@ __global__ void SMFFT_DIT_external(float2* d_input, float2* d_output)
 }
 
 template <class const_params>
-__global__ void SMFFT_DIT_multiple(float2* d_input, float2* d_output)
+__global__ void __launch_bounds__(const_params::fft_length / 4) SMFFT_DIT_multiple(float2* d_input, float2* d_output)
 {
     __shared__ float2 s_input[const_params::fft_sm_required];
     smfft::compat::tile_in<const_params::fft_length>(s_input, d_input);
@@ -219,7 +219,7 @@ __global__ void SMFFT_DIT_multiple(float2* d_input, float2* d_output)
 }
 
 template <class const_params>
-__global__ void FFT_GPU_external(float2* d_input, float2* d_output)
+__global__ void __launch_bounds__(const_params::fft_length / 4) FFT_GPU_external(float2* d_input, float2* d_output)
 {
     extern __shared__ float2 s_input_dyn[];  // FFT_size * 8 bytes (ST:319)
     smfft::compat::tile_in<const_params::fft_length>(s_input_dyn, d_input);
@@ -229,7 +229,7 @@ __global__ void FFT_GPU_external(float2* d_input, float2* d_output)
 }
 
 template <class const_params>
-__global__ void FFT_GPU_multiple(float2* d_input, float2* d_output)
+__global__ void __launch_bounds__(const_params::fft_length / 4) FFT_GPU_multiple(float2* d_input, float2* d_output)
 {
     extern __shared__ float2 s_input_dyn[];
     smfft::compat::tile_in<const_params::fft_length>(s_input_dyn, d_input);
@@ -239,7 +239,7 @@ __global__ void FFT_GPU_multiple(float2* d_input, float2* d_output)
 }
 
 template <class const_params, class const_direction>
-__global__ void FFT_GPU_R2C_C2R_external(float2* d_input, float2* d_output)
+__global__ void __launch_bounds__(const_params::fft_length / 4) FFT_GPU_R2C_C2R_external(float2* d_input, float2* d_output)
 {
     __shared__ float2 s_input[const_params::fft_length + 1];
     smfft::compat::tile_in<const_params::fft_length>(s_input, d_input);
@@ -249,7 +249,7 @@ __global__ void FFT_GPU_R2C_C2R_external(float2* d_input, float2* d_output)
 }
 
 template <class const_params, class const_direction>
-__global__ void FFT_GPU_R2C_C2R_multiple(float2* d_input, float2* d_output)
+__global__ void __launch_bounds__(const_params::fft_length / 4) FFT_GPU_R2C_C2R_multiple(float2* d_input, float2* d_output)
 {
     __shared__ float2 s_input[const_params::fft_length + 1];
     smfft::compat::tile_in<const_params::fft_length>(s_input, d_input);

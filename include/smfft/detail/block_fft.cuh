@@ -69,7 +69,7 @@ struct BlockCfg {
         return s;
     }
     // compact twiddle table (TW_LUT): pass p > 0 owns Ns_p entries W_{Ns_p r_p}^k at tw_offset(p);
-    // the R2C/C2R pair pass owns N/2 + 1 entries W_{2N}^k after them
+    // the R2C/C2R pass owns T entries W_{2N}^t after them (W_{2N}^{t+mT} = W_{2N}^t * W_{2R}^m)
     static SMFFT_CX int tw_offset(int p)
     {
         int o = 0;
@@ -77,7 +77,7 @@ struct BlockCfg {
         return o;
     }
     static constexpr int TW_C2C_ENTRIES = tw_offset((E_ + B_ - 1) / B_);
-    static constexpr int TW_R2C_ENTRIES = (1 << E_) / 2 + 1;
+    static constexpr int TW_R2C_ENTRIES = 1 << (E_ - B_);
 };
 
 // Fill the compact table from the global FP64-rounded table gtw[j] = exp(-2 pi i j / kTwiddleTableSize).
@@ -101,7 +101,7 @@ SMFFT_DEV void fill_twiddle_table(float2* stw, const float2* __restrict__ gtw, i
             for (int k = tid; k < C::TW_R2C_ENTRIES; k += nthreads) {
                 float2 w = plat::ldg_ro(gtw + k * (kTwiddleTableSize / (2 * C::N)));
                 if (R2C_INVERSE) w.y = -w.y;
-                stw[C::TW_C2C_ENTRIES + k] = w;
+                stw[C::TW_C2C_ENTRIES + k] = w;  // W_{2N}^t, t < T (real_pass_regs)
             }
         }
     }
@@ -260,8 +260,58 @@ SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t
     }
 }
 
-// load + all passes; the result is left in registers: v[m] = X[t + m*T] of FFT (tid >> A)
-template <class C, class Hook>
+enum { XF_C2C = 0, XF_R2C = 1, XF_C2R = 2 };  // what one tile computes (kernels::MODE_* use the same values)
+
+// ---- R2C / C2R in registers (RC/FFT-GPU-32bit-Stockham.cu:269-344) ---------
+// N = C::N complex points hold one real transform of length 2N, z[n] = x[2n] + i x[2n+1].
+//   forward : X[k] = H1 + W H2,  H1 = (A + conj B)/2, H2 = -i (A - conj B)/2,  A = Z[k], B = Z[N-k],
+//             W = exp(-2 pi i k / 2N), k = 1..N-1;  bin 0 packs (X[0], X[N]) = (Z0.re + Z0.im, Z0.re - Z0.im)
+//   inverse : the same with conjugated constants, bin 0 un-packed first
+// The reference does this as a separate shared-memory pass over pairs (k, N-k).  Here a thread keeps
+// its own 16 values in registers, reads only the 16 partners B from shared memory, and evaluates the
+// formula for its own k (every pair is evaluated from both ends: more FMAs, half the shared traffic,
+// no extra write-back pass).  The twiddle is one table/MUFU value W^t times the constant W_{2R}^m.
+template <class C, int INVERSE>
+SMFFT_DEV float2 real_combine(float2 A, float2 B, float2 W)
+{
+    constexpr float hx = INVERSE ? -0.5f : 0.5f, hy = INVERSE ? 0.5f : -0.5f;
+    float2 H1, H2;
+    H1.x = 0.5f * (A.x + B.x);
+    H1.y = 0.5f * (A.y - B.y);
+    H2.x = hx * (A.y + B.y);
+    H2.y = hy * (A.x - B.x);
+    const float2 WH = cmul(W, H2);
+    return make_float2(H1.x + WH.x, H1.y + WH.y);
+}
+
+// v[m] holds element k = t + m*T of the tile state `s` (natural order, entry layout); on return
+// v[m] = combined value for k.  `s` is only read.
+template <class C, int INVERSE>
+SMFFT_DEV void real_pass_regs(float2 (&v)[C::R], const float2* s, int fbase, int t, const float2* tw)
+{
+    static_assert(2 * C::R <= 32, "constant twiddles W_{2R}^m come from the W_32 table");
+    float2 wt;
+    if constexpr (C::TW == TW_LUT)
+        wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
+    else
+        wt = tw_mufu<INVERSE, 2 * C::N>(t);
+    static_for<C::R>([&](auto MI) {
+        constexpr int m = decltype(MI)::value;
+        const int k = t + m * C::T;
+        const int kb = (m == 0 && t == 0) ? 0 : C::N - k;  // bin 0 has no partner
+        const float2 Bv = plat::lds64(s + C::Layout::phys(fbase + kb));
+        const float2 W = mul_wconst<INVERSE, m, 2 * C::R>(wt);
+        float2 out = real_combine<C, INVERSE>(v[m], Bv, W);
+        if (m == 0 && t == 0) {
+            const float sc = INVERSE ? 0.5f : 1.0f;
+            out = make_float2(sc * (v[0].x + v[0].y), sc * (v[0].x - v[0].y));
+        }
+        v[m] = out;
+    });
+}
+
+// load (+ C2R pre-pass) + all FFT passes; the result is left in registers: v[m] = X[t + m*T] of FFT (tid >> A)
+template <class C, int XF, class Hook>
 SMFFT_DEV void block_fft_regs(float2 (&v)[C::R], float2* s, const float2* tw, Hook&& hook)
 {
     const int tid = plat::tid();
@@ -270,6 +320,7 @@ SMFFT_DEV void block_fft_regs(float2 (&v)[C::R], float2* s, const float2* tw, Ho
     int vt = t;
     if constexpr (C::REORDER) {
         load_natural<C>(v, s, fbase, t);
+        if constexpr (XF == XF_C2R) real_pass_regs<C, 1>(v, s, fbase, t, tw);  // tile is read-only here: no barrier
     } else {
         vt = noreorder_vid<C>(t);
         load_rows_brev<C>(v, s, fbase, vt);
@@ -277,28 +328,47 @@ SMFFT_DEV void block_fft_regs(float2 (&v)[C::R], float2* s, const float2* tw, Ho
     run_passes<C, 0>(v, s, fbase, vt, t, tw, hook);
 }
 
-// In-place FFT of all F transforms of the tile.  Contract: the tile is visible to the whole CTA on
-// entry (caller synchronised); on return each thread has written only slots it read in the last
-// pass, so the caller must synchronise before other threads (or the async proxy) read the tile.
+// R2C tail: Z (registers) -> tile -> barrier -> partners read back -> X in registers
 template <class C>
+SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
+{
+    const int tid = plat::tid();
+    const int t = tid & (C::T - 1);
+    const int fbase = (tid >> C::A) << C::E;
+    // same layout: these are the slots this thread read in the last pass, no barrier needed before
+    if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+    store_natural<C>(v, s, fbase, t);
+    plat::sync_block();
+    real_pass_regs<C, 0>(v, s, fbase, t, tw);
+}
+
+// In-place transform of all F transforms of the tile (XF_C2C / XF_R2C / XF_C2R).  Contract: the tile
+// is visible to the whole CTA on entry; on return the caller must synchronise before other threads
+// (or the async proxy) read the tile.
+template <class C, int XF = XF_C2C>
 SMFFT_DEV void block_fft_tile(float2* s, const float2* tw)
 {
     float2 v[C::R];
-    block_fft_regs<C>(v, s, tw, NoHook{});
+    block_fft_regs<C, XF>(v, s, tw, NoHook{});
     const int tid = plat::tid();
-    // with distinct entry/exchange layouts the final slots are not the ones this thread just read
-    if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+    if constexpr (XF == XF_R2C) {
+        r2c_tail_regs<C>(v, s, tw);
+        plat::sync_block();  // every partner has been read before the packed spectrum overwrites Z
+    } else {
+        // with distinct entry/exchange layouts the final slots are not the ones this thread just read
+        if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+    }
     store_natural<C>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
 }
 
 // Same transform, result written straight from registers to global memory (coalesced 8-byte
 // stores: consecutive threads own consecutive points).  g = start of this tile in the output.
-template <class C, class Hook>
-SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid,
-                                        Hook&& hook)
+template <class C, int XF, class Hook>
+SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid, Hook&& hook)
 {
     float2 v[C::R];
-    block_fft_regs<C>(v, s, tw, hook);
+    block_fft_regs<C, XF>(v, s, tw, hook);
+    if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
     const int tid = plat::tid();
     const int x0 = ((tid >> C::A) << C::E) + (tid & (C::T - 1));
     if (valid >= C::L) {
@@ -314,7 +384,7 @@ SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __r
     }
 }
 
-// ---- R2C / C2R pair pass (RC/FFT-GPU-32bit-Stockham.cu:269-344) ----------
+// ---- R2C / C2R pair pass, shared-memory form (used by include/smfft/compat.cuh, 4 points/thread) ----
 // M = C::N complex points hold one real transform of length 2M.  Each FFT has M/2 pairs (k, M-k),
 // k = 1..M/2, spread over its T threads (R/2 pairs per thread), plus bin 0 on thread 0.
 // INVERSE = 0: call after the forward C2C;  INVERSE = 1: call before the inverse C2C.
@@ -343,10 +413,8 @@ SMFFT_DEV void r2c_pair_pass_tile(float2* s, const float2* tw)
         H1.y = 0.5f * (Av.y - Bv.y);
         H2.x = hx * (Av.y + Bv.y);
         H2.y = hy * (Av.x - Bv.x);
-        if constexpr (C::TW == TW_LUT)
-            W = plat::lds64(tw + C::TW_C2C_ENTRIES + k);
-        else
-            W = tw_mufu<INVERSE, 2 * M>(k);
+        static_assert(C::TW == TW_MUFU, "the pair-pass form is only used by the reference-contract API (MUFU twiddles)");
+        W = tw_mufu<INVERSE, 2 * M>(k);
         const float2 WH = cmul(W, H2);
         plat::sts64(pa, make_float2(H1.x + WH.x, H1.y + WH.y));
         if (k != M - k) plat::sts64(pb, make_float2(H1.x - WH.x, -H1.y + WH.y));

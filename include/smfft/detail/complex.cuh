@@ -19,8 +19,13 @@ SMFFT_DEV void static_for(F&& f)
     static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
 }
 
+#if defined(SMFFT_PACKED_F32X2) && !defined(SMFFT_EMU)
+SMFFT_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+SMFFT_DEV float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+#else
 SMFFT_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SMFFT_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 SMFFT_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 SMFFT_DEV float2 csqr(float2 a) { return make_float2(a.x * a.x - a.y * a.y, 2.0f * a.x * a.y); }
 

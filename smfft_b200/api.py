@@ -21,7 +21,8 @@ class SmfftError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_PKG, "lib", "libsmfft.so")
+    # SMFFT_LIB selects an experiment build of the same CUDA library (smfft_b200/build.py, SMFFT_VARIANT)
+    return os.environ.get("SMFFT_LIB") or os.path.join(_PKG, "lib", "libsmfft.so")
 
 
 def lib() -> ctypes.CDLL:

@@ -16,8 +16,10 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "lib", "obj")
-LIB = os.path.join(PKG, "lib", "libsmfft.so")
+# experiment builds: SMFFT_VARIANT=name SMFFT_EXTRA_NVFLAGS="-D..." -> lib/libsmfft_name.so (load with SMFFT_LIB=path)
+VARIANT = os.environ.get("SMFFT_VARIANT", "")
+OBJ = os.path.join(PKG, "lib", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(PKG, "lib", "libsmfft" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("SMFFT_NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
@@ -25,7 +27,7 @@ NVFLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     f"-I{os.path.join(ROOT, 'include')}", f"-I{CSRC}",
-]
+] + os.environ.get("SMFFT_EXTRA_NVFLAGS", "").split()
 
 
 def _deps():
@@ -67,7 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(f"linked {LIB}")
-    _build_compat(force)
+    if not VARIANT:
+        _build_compat(force)
     return LIB
 
 

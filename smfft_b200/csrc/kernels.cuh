@@ -19,7 +19,7 @@ namespace smfft {
 namespace kernels {
 
 enum { IO_TMA = 0, IO_LDG = 1, IO_TMA_STG = 2 };  // TMA_STG: TMA loads, results stored from registers
-enum { MODE_C2C = 0, MODE_R2C = 1, MODE_C2R = 2 };
+enum { MODE_C2C = detail::XF_C2C, MODE_R2C = detail::XF_R2C, MODE_C2R = detail::XF_C2R };
 
 struct TileArgs {
     plat::TensorMap in_map;   // IO_TMA: [rows][32 x f32], box = tile rows, SWIZZLE_128B
@@ -32,34 +32,23 @@ struct TileArgs {
     int l2_hint;              // bit 0: TMA loads evict_first, bit 1: TMA stores evict_first
 };
 
-// the per-tile transform; tile visible on entry, caller synchronises after
+// the per-tile transform, in place in shared memory; tile visible on entry, caller synchronises after
 template <class C, int MODE, int REPS>
 SMFFT_DEV void tile_transform(float2* s, const float2* tw)
 {
 #pragma unroll 1
     for (int rep = 0; rep < REPS; rep++) {
-        if constexpr (MODE == MODE_C2C) {
-            detail::block_fft_tile<C>(s, tw);
-        } else if constexpr (MODE == MODE_R2C) {
-            detail::block_fft_tile<C>(s, tw);
-            plat::sync_block();
-            detail::r2c_pair_pass_tile<C, 0>(s, tw);
-        } else {
-            detail::r2c_pair_pass_tile<C, 1>(s, tw);
-            plat::sync_block();
-            detail::block_fft_tile<C>(s, tw);
-        }
+        detail::block_fft_tile<C, MODE>(s, tw);
         if (rep + 1 < REPS) plat::sync_block();
     }
 }
 
-// same transform with the result stored straight from registers (C2C and C2R only); hook: see
-// detail::run_passes.  REPS == 0 is the staging-only ceiling measurement (tools/tune).
+// same transform with the result stored straight from registers; hook: see detail::run_passes.
+// REPS == 0 is the staging-only ceiling measurement (tools/tune).
 template <class C, int MODE, int REPS, class Hook>
 SMFFT_DEV void tile_transform_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid,
                                         Hook&& hook)
 {
-    static_assert(MODE != MODE_R2C, "the R2C pair pass runs in shared memory after the FFT");
     if constexpr (REPS == 0) {
         float2 v[C::R];
         const int tid = plat::tid();
@@ -72,11 +61,7 @@ SMFFT_DEV void tile_transform_to_global(float2* s, const float2* tw, float2* __r
             if (fbase + t + m * C::T < valid) plat::stg64_stream(g + fbase + t + m * C::T, v[m]);
         });
     } else {
-        if constexpr (MODE == MODE_C2R) {
-            detail::r2c_pair_pass_tile<C, 1>(s, tw);
-            plat::sync_block();
-        }
-        detail::block_fft_tile_to_global<C>(s, tw, g, valid, hook);
+        detail::block_fft_tile_to_global<C, MODE>(s, tw, g, valid, hook);
     }
 }
 

@@ -28,7 +28,7 @@ namespace host {
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 static std::mutex g_mu;
-static int g_opt_io = kernels::IO_TMA;
+static int g_opt_io = 0;  // 0 auto (measured best TMA staging per size), 1 LDG, 2 TMA in+out, 3 TMA in / registers out
 static int g_opt_tw = TW_LUT;
 static int g_opt_quirk4096 = 0;
 static int g_opt_ctas_per_sm = 0;
@@ -86,6 +86,7 @@ static int get_device_state(DeviceState** out)
     return 0;
 }
 
+// io: kernels::IO_* or -1 = the preferred TMA staging of this size and mode
 static const KernelEntry* find_entry(int mode, int e, int dir, int reorder, int io, int tw, int reps)
 {
     EntryList l{nullptr, 0};
@@ -102,7 +103,8 @@ static const KernelEntry* find_entry(int mode, int e, int dir, int reorder, int 
     }
     for (int i = 0; i < l.count; i++) {
         const KernelEntry& k = l.entries[i];
-        if (k.mode == mode && k.dir == dir && k.reorder == reorder && k.io == io && k.tw == tw && k.reps == reps) return &k;
+        if (k.mode != mode || k.dir != dir || k.reorder != reorder || k.tw != tw || k.reps != reps) continue;
+        if (io >= 0 ? k.io == io : k.prefer) return &k;
     }
     return nullptr;
 }
@@ -128,12 +130,13 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     if (get_device_state(&ds)) return 1;
     if (n_points <= 0) return 0;
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail("smfft: device pointers must be 16-byte aligned");
-    int io = reps > 1 ? kernels::IO_LDG : g_opt_io;
+    int io = reps > 1 ? kernels::IO_LDG
+                      : g_opt_io == 0 ? -1 : g_opt_io == 1 ? kernels::IO_LDG : g_opt_io == 2 ? kernels::IO_TMA : kernels::IO_TMA_STG;
     const KernelEntry* k = find_entry(mode, e, dir, reorder, io, g_opt_tw, reps);
-    if (k && io == kernels::IO_TMA && n_points < k->tile_points) {  // batch smaller than one tile: thread staging, no tensor map
-        io = kernels::IO_LDG;
-        k = find_entry(mode, e, dir, reorder, io, g_opt_tw, reps);
-    }
+    if (!k && io == kernels::IO_TMA_STG) k = find_entry(mode, e, dir, reorder, kernels::IO_TMA, g_opt_tw, reps);
+    if (k && k->io != kernels::IO_LDG && n_points < k->tile_points)  // batch smaller than one tile: thread staging, no tensor map
+        k = find_entry(mode, e, dir, reorder, kernels::IO_LDG, g_opt_tw, reps);
+    if (k) io = k->io;
     if (!k) return fail("smfft: no kernel instance for mode %d, 2^%d points, dir %d, reorder %d, io %d, tw %d, reps %d", mode, e, dir, reorder, io, g_opt_tw, reps);
 
     bool need_attr = true;
@@ -150,15 +153,17 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     args.gin = (const float2*)d_in;
     args.gout = (float2*)d_out;
     args.tw = ds->tw;
-    if (io == kernels::IO_TMA) {
+    if (io != kernels::IO_LDG) {
         if (make_map(&args.in_map, d_in, n_points / 16, k->tile_points / 16)) return 1;
-        if (make_map(&args.out_map, d_out, n_points / 16, k->tile_points / 16)) return 1;
+        if (io == kernels::IO_TMA && make_map(&args.out_map, d_out, n_points / 16, k->tile_points / 16)) return 1;
     }
-    int per_sm = g_opt_ctas_per_sm;
-    if (per_sm <= 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k->func, k->threads, k->smem_bytes));
-        if (per_sm <= 0) return fail("smfft: kernel does not fit on an SM (smem %d B, %d threads)", k->smem_bytes, k->threads);
-    }
+    // persistent grid: SMs x CTAs/SM.  The TMA kernels are launched with the measured load concurrency
+    // (tuning.hpp), never more than fits; everything else fills the SM.
+    int fit = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, k->func, k->threads, k->smem_bytes));
+    if (fit <= 0) return fail("smfft: kernel does not fit on an SM (smem %d B, %d threads)", k->smem_bytes, k->threads);
+    int per_sm = g_opt_ctas_per_sm > 0 ? g_opt_ctas_per_sm : (k->ctas > 0 ? k->ctas : fit);
+    if (per_sm > fit) per_sm = fit;
     long long grid = (long long)ds->sms * per_sm;
     if (grid > args.n_tiles) grid = args.n_tiles;
     void* params[] = {&args};
@@ -249,7 +254,7 @@ int smfft_set_stream(void* stream)
 
 int smfft_set_option(const char* key, int value)
 {
-    if (!strcmp(key, "io")) { if (value < 0 || value > 1) return fail("io must be 0 or 1"); g_opt_io = value; return 0; }
+    if (!strcmp(key, "io")) { if (value < 0 || value > 3) return fail("io must be 0..3"); g_opt_io = value; return 0; }
     if (!strcmp(key, "twiddle")) { if (value < 0 || value > 1) return fail("twiddle must be 0 or 1"); g_opt_tw = value; return 0; }
     if (!strcmp(key, "quirk_4096")) { g_opt_quirk4096 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }

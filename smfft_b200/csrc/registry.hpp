@@ -11,6 +11,8 @@ namespace host {
 struct KernelEntry {
     int mode, e, dir, reorder, io, tw, reps;  // lookup key (e = log2 of the complex length)
     int tile_points, threads, smem_bytes, minb, stages;
+    int ctas;    // CTAs per SM to launch (0 = occupancy limit)
+    int prefer;  // 1 = the measured best staging for this size and mode
     const void* func;
 };
 
@@ -28,7 +30,7 @@ KernelEntry make_entry_shape()
     KernelEntry k;
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
     k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();
-    k.minb = MINB; k.stages = ST;
+    k.minb = MINB; k.stages = ST; k.ctas = 0; k.prefer = 0;
     k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB>);
     return k;
 }
@@ -38,7 +40,12 @@ template <int E, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
 KernelEntry make_entry()
 {
     using Tn = kernels::Tuning<E>;
-    return make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS>();
+    KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS>();
+    k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
+    // R2C always leaves from registers (its tail already has the spectrum there); C2C / C2R per tuning
+    constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C || Tn::STG);
+    k.prefer = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);
+    return k;
 }
 
 // every instance the C ABI can dispatch to for one size
@@ -46,7 +53,7 @@ template <int E>
 EntryList build_entries()
 {
     using namespace kernels;
-    static KernelEntry tab[64];
+    static KernelEntry tab[96];
     static int n = 0;
     if (n == 0) {
         int i = 0;
@@ -60,6 +67,15 @@ EntryList build_entries()
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 1);
         SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_MUFU, 1);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_MUFU, 1);
+        // register-output staging (TMA in, STG out), C2C and C2R
+        if constexpr (Tuning<E>::STAGES >= 2) {
+            SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_LUT, 1);
+            SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_LUT, 1);
+            SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_MUFU, 1);
+            SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_MUFU, 1);
+            SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_MUFU, 1);
+            SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_MUFU, 1);
+        }
         // C2C multiple (FFT_multiple_benchmark, 100 reps in place): compute-bound, LDG staging only
         SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_LUT, 100);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 100);

@@ -3,47 +3,45 @@
 //
 //   B      log2 points per thread (R = 16: radix-16 register passes)
 //   TILE_E log2 points per tile; a tile is F = 2^(TILE_E-E) whole FFTs, THREADS = 2^(TILE_E-B)
-//   STAGES tile buffers per CTA on the TMA path (load k+1 / FFT k / store k-1 overlap)
-//   MINB   CTAs per SM the kernel is compiled for (__launch_bounds__)
-// Values are the measured best of tools/tune on a B200, 4 GiB batch (profiles/r01_tune_shapes_a.csv:
-// 450 variants, every one checked against the default shape's output).  All shapes within ~3 % of
-// each other at 1.32-1.42 ms; the LDG-staged variants of the same shapes take 2.1-3.1 ms.
+//   STAGES tile buffers per CTA on the TMA paths (load k+1 overlaps the FFT of tile k)
+//   MINB   CTAs per SM the kernel is compiled for (__launch_bounds__ register cap)
+//   CTAS   CTAs per SM the persistent grid is launched with
+//   STG    1 = results leave from registers (IO_TMA_STG) for C2C / C2R, 0 = TMA stores
+//
+// What the measurements say (profiles/r01_tune_*.csv, profiles/r01_copylab_*.csv, B200, 4 GiB batch):
+//   * the FFT arithmetic is fully hidden: a staging-only kernel (tile in, tile out) costs the same;
+//   * the memory system wants 48-64 KB of outstanding TMA loads per SM: CTAS x (STAGES-1) x tile
+//     bytes.  32 KB is too little (1.4-1.5 ms), >= 96 KB is too much (1.36-1.40 ms), the sweet spot
+//     gives 1.27-1.30 ms for a pure copy and 1.28-1.32 ms for the FFT (cudaMemcpy D2D: 1.30 ms);
+//   * hence two CTAs of 256 threads with two 32 KB buffers each (three CTAs x 16 KB for N <= 64).
 #pragma once
 
 namespace smfft {
 namespace kernels {
 
 template <int E>
-struct Tuning {  // N = 256 and below: 4 CTAs/SM x one 32 KB tile buffer
-    static constexpr int B = 4;
-    static constexpr int TILE_E = 12;
-    static constexpr int F = 1 << (TILE_E - E);
-    static constexpr int STAGES = 1;
-    static constexpr int MINB = 4;
+struct Tuning {  // N >= 1024
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - E), STAGES = 2, MINB = 2, CTAS = 2, STG = 0;
 };
 template <>
 struct Tuning<5> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 5), STAGES = 2, MINB = 2;
+    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 5), STAGES = 2, MINB = 4, CTAS = 3, STG = 0;
+};
+template <>
+struct Tuning<6> {
+    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 6), STAGES = 2, MINB = 4, CTAS = 3, STG = 0;
 };
 template <>
 struct Tuning<7> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 7), STAGES = 2, MINB = 2;
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 7), STAGES = 2, MINB = 2, CTAS = 2, STG = 1;
+};
+template <>
+struct Tuning<8> {
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 8), STAGES = 2, MINB = 2, CTAS = 2, STG = 1;
 };
 template <>
 struct Tuning<9> {
-    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 9), STAGES = 2, MINB = 4;
-};
-template <>
-struct Tuning<10> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 10), STAGES = 3, MINB = 2;
-};
-template <>
-struct Tuning<11> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 11), STAGES = 3, MINB = 2;
-};
-template <>
-struct Tuning<12> {
-    static constexpr int B = 4, TILE_E = 12, F = 1, STAGES = 2, MINB = 3;
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 9), STAGES = 2, MINB = 2, CTAS = 2, STG = 1;
 };
 
 }  // namespace kernels

@@ -198,6 +198,7 @@ static int run_shape(const float2* in, float2* out, long long n_ffts, int dir, i
         if constexpr (STAGES >= 2) { CASE(0, 1, 2, 0) CASE(0, 0, 2, 0) CASE(1, 1, 2, 0) CASE(1, 0, 2, 0) CASE(0, 1, 2, 1) }
     } else if constexpr (MODE == kernels::MODE_R2C) {
         CASE(0, 1, 0, 0) CASE(0, 1, 1, 0) CASE(0, 1, 0, 1)
+        if constexpr (STAGES >= 2) { CASE(0, 1, 2, 0) }
     } else {
         CASE(1, 1, 0, 0) CASE(1, 1, 1, 0) CASE(1, 1, 0, 1)
         if constexpr (STAGES >= 2) { CASE(1, 1, 2, 0) }

@@ -52,7 +52,7 @@ def run_c2c(sm, x, inverse, reorder):
     return c64(dy)
 
 
-@pytest.mark.parametrize("io", [0, 1])
+@pytest.mark.parametrize("io", [0, 1, 2, 3])   # auto / thread-staged / TMA in+out / TMA in, registers out
 @pytest.mark.parametrize("tw", [0, 1])
 @pytest.mark.parametrize("n", SIZES)
 def test_c2c_vs_oracle(sm, n, io, tw):
@@ -92,7 +92,7 @@ def test_quirk_4096_switch(sm):
 
 
 @pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])
-@pytest.mark.parametrize("io", [0, 1])
+@pytest.mark.parametrize("io", [0, 1, 2, 3])
 def test_r2c_c2r_vs_oracle(sm, n, io):
     sm.set_option("io", io)
     nf = 2 * (8192 // n) + 3
