@@ -101,7 +101,7 @@ SMFFT_DEV void fill_twiddle_table(float2* stw, const float2* __restrict__ gtw, i
             for (int k = tid; k < C::TW_R2C_ENTRIES; k += nthreads) {
                 float2 w = plat::ldg_ro(gtw + k * (kTwiddleTableSize / (2 * C::N)));
                 if (R2C_INVERSE) w.y = -w.y;
-                stw[C::TW_C2C_ENTRIES + k] = w;  // W_{2N}^t, t < T (real_pass_regs)
+                stw[C::TW_C2C_ENTRIES + k] = make_float2(0.5f * w.x, 0.5f * w.y);  // W_{2N}^t / 2, t < T (real_pass_regs)
             }
         }
     }
@@ -271,17 +271,23 @@ enum { XF_C2C = 0, XF_R2C = 1, XF_C2R = 2 };  // what one tile computes (kernels
 // its own 16 values in registers, reads only the 16 partners B from shared memory, and evaluates the
 // formula for its own k (every pair is evaluated from both ends: more FMAs, half the shared traffic,
 // no extra write-back pass).  The twiddle is one table/MUFU value W^t times the constant W_{2R}^m.
-template <class C, int INVERSE>
-SMFFT_DEV float2 real_combine(float2 A, float2 B, float2 W)
+// Wh = W/2 (the table stores it pre-scaled).  With s = A + B, d = A - B (componentwise):
+//   forward: X = ( s.x/2 + Wh.x s.y + Wh.y d.x ,  d.y/2 - Wh.x d.x + Wh.y s.y )
+//   inverse: Z = ( s.x/2 - Wh.x s.y - Wh.y d.x ,  d.y/2 + Wh.x d.x - Wh.y s.y )   (Wh already conjugated)
+// -- the reference's H1 + W H2 (RC:292-307) with the constants folded in: 4 adds + 6 FMAs.
+template <int INVERSE>
+SMFFT_DEV float2 real_combine(float2 A, float2 B, float2 Wh)
 {
-    constexpr float hx = INVERSE ? -0.5f : 0.5f, hy = INVERSE ? 0.5f : -0.5f;
-    float2 H1, H2;
-    H1.x = 0.5f * (A.x + B.x);
-    H1.y = 0.5f * (A.y - B.y);
-    H2.x = hx * (A.y + B.y);
-    H2.y = hy * (A.x - B.x);
-    const float2 WH = cmul(W, H2);
-    return make_float2(H1.x + WH.x, H1.y + WH.y);
+    const float sx = A.x + B.x, sy = A.y + B.y, dx = A.x - B.x, dy = A.y - B.y;
+    float2 o;
+    if constexpr (!INVERSE) {
+        o.x = 0.5f * sx + (Wh.x * sy + Wh.y * dx);
+        o.y = 0.5f * dy + (Wh.y * sy - Wh.x * dx);
+    } else {
+        o.x = 0.5f * sx - (Wh.x * sy + Wh.y * dx);
+        o.y = 0.5f * dy - (Wh.y * sy - Wh.x * dx);
+    }
+    return o;
 }
 
 // v[m] holds element k = t + m*T of the tile state `s` (natural order, entry layout); on return
@@ -290,23 +296,37 @@ template <class C, int INVERSE>
 SMFFT_DEV void real_pass_regs(float2 (&v)[C::R], const float2* s, int fbase, int t, const float2* tw)
 {
     static_assert(2 * C::R <= 32, "constant twiddles W_{2R}^m come from the W_32 table");
-    float2 wt;
-    if constexpr (C::TW == TW_LUT)
+    float2 wt;  // W_{2N}^t / 2
+    if constexpr (C::TW == TW_LUT) {
         wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
-    else
+    } else {
         wt = tw_mufu<INVERSE, 2 * C::N>(t);
+        wt.x *= 0.5f;
+        wt.y *= 0.5f;
+    }
+    const int xp = fbase + C::N - t;  // partner of k = t + m*T is N - k = (N - t) - m*T
+    // W^{t+mT}/2 = wt * W_{2R}^m; the upper half of the m range is the lower half times a quarter turn (free)
+    float2 wm[C::R];
+    static_for<C::R / 2>([&](auto MI) {
+        constexpr int m = decltype(MI)::value;
+        wm[m] = mul_wconst<INVERSE, m, 2 * C::R>(wt);
+        wm[m + C::R / 2] = mul_wconst<INVERSE, 1, 4>(wm[m]);
+    });
     static_for<C::R>([&](auto MI) {
         constexpr int m = decltype(MI)::value;
-        const int k = t + m * C::T;
-        const int kb = (m == 0 && t == 0) ? 0 : C::N - k;  // bin 0 has no partner
-        const float2 Bv = plat::lds64(s + C::Layout::phys(fbase + kb));
-        const float2 W = mul_wconst<INVERSE, m, 2 * C::R>(wt);
-        float2 out = real_combine<C, INVERSE>(v[m], Bv, W);
-        if (m == 0 && t == 0) {
-            const float sc = INVERSE ? 0.5f : 1.0f;
-            out = make_float2(sc * (v[0].x + v[0].y), sc * (v[0].x - v[0].y));
+        if constexpr (m == 0) {
+            // t == 0 owns bin 0, which has no partner: (X[0], X[N]) packed / un-packed (RC:280-286, 332-340)
+            const float2 Bv = plat::lds64(s + C::Layout::phys(t == 0 ? fbase : xp));
+            float2 out = real_combine<INVERSE>(v[0], Bv, wm[0]);
+            if (t == 0) {
+                const float sc = INVERSE ? 0.5f : 1.0f;
+                out = make_float2(sc * (v[0].x + v[0].y), sc * (v[0].x - v[0].y));
+            }
+            v[0] = out;
+        } else {
+            const float2 Bv = plat::lds64(s + C::Layout::phys(xp - m * C::T));
+            v[m] = real_combine<INVERSE>(v[m], Bv, wm[m]);
         }
-        v[m] = out;
     });
 }
 

@@ -381,8 +381,54 @@ int smfft_r2c_c2r_host(const void* h_in, void* h_out, int fft_size, long long n_
     return host_driver(1, h_in, h_out, fft_size, n_ffts, inverse, 1, n_runs, single_ms, multi_ms);
 }
 
-// Chunked pipeline: chunk i's H2D, FFT and D2H run on three streams chained by events, two device
-// buffer pairs in rotation, so PCIe in both directions and the SMs overlap.
+// Chunked pipeline: chunk i's H2D, FFT and D2H run on three streams chained by events, three device
+// buffer pairs in rotation, so PCIe in both directions and the SMs overlap.  Buffers, streams and
+// events are created once and kept (per process) so repeated calls pay no allocation.
+namespace {
+struct PipelineCtx {
+    static const int NBUF = 3;
+    size_t cap = 0;
+    int device = -1;
+    void* d_in[NBUF] = {nullptr, nullptr, nullptr};
+    void* d_out[NBUF] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_fft = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[NBUF], ev_fft[NBUF], ev_out[NBUF], t0, t1;
+    bool ready = false;
+};
+PipelineCtx g_pipe;
+
+int pipeline_prepare(size_t chunk_bytes)
+{
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    PipelineCtx& p = g_pipe;
+    if (p.ready && p.device == dev && p.cap >= chunk_bytes) return 0;
+    if (p.ready) {
+        for (int i = 0; i < PipelineCtx::NBUF; i++) { cudaFree(p.d_in[i]); cudaFree(p.d_out[i]); p.d_in[i] = p.d_out[i] = nullptr; }
+    } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.s_fft, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < PipelineCtx::NBUF; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.ev_fft[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.ev_out[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreate(&p.t0));
+        CUDA_TRY(cudaEventCreate(&p.t1));
+    }
+    p.ready = false;
+    for (int i = 0; i < PipelineCtx::NBUF; i++) {
+        CUDA_TRY(cudaMalloc(&p.d_in[i], chunk_bytes));
+        CUDA_TRY(cudaMalloc(&p.d_out[i], chunk_bytes));
+    }
+    p.cap = chunk_bytes;
+    p.device = dev;
+    p.ready = true;
+    return 0;
+}
+}  // namespace
+
 int smfft_pipeline_host(const void* h_in, void* h_out, int fft_size, long long n_ffts, int inverse, int reorder, int mode,
                         long long chunk_ffts, double* ms)
 {
@@ -390,28 +436,17 @@ int smfft_pipeline_host(const void* h_in, void* h_out, int fft_size, long long n
     if (get_device_state(&ds)) return 1;
     if (mode < 0 || mode > 2) return fail("smfft: pipeline mode must be 0 (C2C), 1 (R2C) or 2 (C2R)");
     const size_t fft_bytes = (size_t)fft_size * (mode == 0 ? sizeof(float2) : sizeof(float));
-    if (chunk_ffts <= 0) chunk_ffts = (long long)((256u << 20) / fft_bytes);
+    if (chunk_ffts <= 0) chunk_ffts = (long long)((128u << 20) / fft_bytes);
     if (chunk_ffts > n_ffts) chunk_ffts = n_ffts;
-    const int NBUF = 3;
-    void *d_in[NBUF] = {nullptr, nullptr, nullptr}, *d_out[NBUF] = {nullptr, nullptr, nullptr};
-    cudaStream_t s_in, s_fft, s_out;
-    cudaEvent_t ev_in[NBUF], ev_fft[NBUF], ev_out[NBUF], t0, t1;
+    if (n_ffts <= 0) return 0;
+    if (pipeline_prepare((size_t)chunk_ffts * fft_bytes)) return 1;
+    PipelineCtx& p = g_pipe;
+    const int NBUF = PipelineCtx::NBUF;
     int rc = 0;
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_fft, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < NBUF; i++) {
-        CUDA_TRY(cudaMalloc(&d_in[i], chunk_ffts * fft_bytes));
-        CUDA_TRY(cudaMalloc(&d_out[i], chunk_ffts * fft_bytes));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_fft[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaEventCreate(&t0));
-    CUDA_TRY(cudaEventCreate(&t1));
     cudaStream_t saved = g_stream;
-    CUDA_TRY(cudaEventRecord(t0, s_in));
-    CUDA_TRY(cudaStreamWaitEvent(s_out, t0, 0));
+    CUDA_TRY(cudaEventRecord(p.t0, p.s_in));
+    CUDA_TRY(cudaStreamWaitEvent(p.s_out, p.t0, 0));
+    CUDA_TRY(cudaStreamWaitEvent(p.s_fft, p.t0, 0));
     long long done = 0;
     for (long long i = 0; done < n_ffts && !rc; i++, done += chunk_ffts) {
         const int b = (int)(i % NBUF);
@@ -419,39 +454,32 @@ int smfft_pipeline_host(const void* h_in, void* h_out, int fft_size, long long n
         const char* src = (const char*)h_in + (size_t)done * fft_bytes;
         char* dst = (char*)h_out + (size_t)done * fft_bytes;
         if (i >= NBUF) {
-            cudaStreamWaitEvent(s_in, ev_fft[b], 0);   // d_in[b] consumed by the FFT of chunk i-NBUF
-            cudaStreamWaitEvent(s_fft, ev_out[b], 0);  // d_out[b] drained by the D2H of chunk i-NBUF
+            cudaStreamWaitEvent(p.s_in, p.ev_fft[b], 0);   // d_in[b] consumed by the FFT of chunk i-NBUF
+            cudaStreamWaitEvent(p.s_fft, p.ev_out[b], 0);  // d_out[b] drained by the D2H of chunk i-NBUF
         }
-        cudaMemcpyAsync(d_in[b], src, cnt * fft_bytes, cudaMemcpyHostToDevice, s_in);
-        cudaEventRecord(ev_in[b], s_in);
-        cudaStreamWaitEvent(s_fft, ev_in[b], 0);
-        g_stream = s_fft;
-        rc = mode == 0 ? smfft_exec_c2c(d_in[b], d_out[b], fft_size, cnt, inverse, reorder)
-                       : smfft_exec_r2c_c2r(d_in[b], d_out[b], fft_size, cnt, mode == 2);
+        cudaMemcpyAsync(p.d_in[b], src, cnt * fft_bytes, cudaMemcpyHostToDevice, p.s_in);
+        cudaEventRecord(p.ev_in[b], p.s_in);
+        cudaStreamWaitEvent(p.s_fft, p.ev_in[b], 0);
+        g_stream = p.s_fft;
+        rc = mode == 0 ? smfft_exec_c2c(p.d_in[b], p.d_out[b], fft_size, cnt, inverse, reorder)
+                       : smfft_exec_r2c_c2r(p.d_in[b], p.d_out[b], fft_size, cnt, mode == 2);
         g_stream = saved;
-        cudaEventRecord(ev_fft[b], s_fft);
-        cudaStreamWaitEvent(s_out, ev_fft[b], 0);
-        cudaMemcpyAsync(dst, d_out[b], cnt * fft_bytes, cudaMemcpyDeviceToHost, s_out);
-        cudaEventRecord(ev_out[b], s_out);
+        cudaEventRecord(p.ev_fft[b], p.s_fft);
+        cudaStreamWaitEvent(p.s_out, p.ev_fft[b], 0);
+        cudaMemcpyAsync(dst, p.d_out[b], cnt * fft_bytes, cudaMemcpyDeviceToHost, p.s_out);
+        cudaEventRecord(p.ev_out[b], p.s_out);
     }
-    cudaEventRecord(t1, s_out);
-    cudaError_t es = cudaEventSynchronize(t1);
-    cudaStreamSynchronize(s_in);
-    cudaStreamSynchronize(s_fft);
+    cudaEventRecord(p.t1, p.s_out);
+    cudaError_t es = cudaEventSynchronize(p.t1);
+    cudaStreamSynchronize(p.s_in);
+    cudaStreamSynchronize(p.s_fft);
     if (!rc && es != cudaSuccess) rc = fail("smfft: pipeline failed: %s", cudaGetErrorString(es));
     if (!rc && ms) {
         float t = 0;
-        cudaEventElapsedTime(&t, t0, t1);
+        cudaEventElapsedTime(&t, p.t0, p.t1);
         *ms += (double)t;
     }
-    for (int i = 0; i < NBUF; i++) {
-        cudaFree(d_in[i]); cudaFree(d_out[i]);
-        cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_fft[i]); cudaEventDestroy(ev_out[i]);
-    }
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
-    cudaStreamDestroy(s_in); cudaStreamDestroy(s_fft); cudaStreamDestroy(s_out);
     return rc;
 }
 
-#pragma GCC visibility pop
 }  // extern "C"

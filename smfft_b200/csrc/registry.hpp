@@ -42,8 +42,7 @@ KernelEntry make_entry()
     using Tn = kernels::Tuning<E>;
     KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS>();
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
-    // R2C always leaves from registers (its tail already has the spectrum there); C2C / C2R per tuning
-    constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C || Tn::STG);
+    constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
     k.prefer = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);
     return k;
 }

@@ -6,7 +6,8 @@
 //   STAGES tile buffers per CTA on the TMA paths (load k+1 overlaps the FFT of tile k)
 //   MINB   CTAs per SM the kernel is compiled for (__launch_bounds__ register cap)
 //   CTAS   CTAs per SM the persistent grid is launched with
-//   STG    1 = results leave from registers (IO_TMA_STG) for C2C / C2R, 0 = TMA stores
+//   STG / STG_R2C / STG_C2R   1 = results leave from registers (IO_TMA_STG), 0 = TMA stores, per transform kind
+//          (register stores need T >= 16 threads per FFT to stay coalesced: not for N <= 128)
 //
 // What the measurements say (profiles/r01_tune_*.csv, profiles/r01_copylab_*.csv, B200, 4 GiB batch):
 //   * the FFT arithmetic is fully hidden: a staging-only kernel (tile in, tile out) costs the same;
@@ -21,27 +22,27 @@ namespace kernels {
 
 template <int E>
 struct Tuning {  // N >= 1024
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - E), STAGES = 2, MINB = 2, CTAS = 2, STG = 0;
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - E), STAGES = 2, MINB = 2, CTAS = 2, STG = 0, STG_R2C = 1, STG_C2R = 0;
 };
 template <>
 struct Tuning<5> {
-    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 5), STAGES = 2, MINB = 4, CTAS = 3, STG = 0;
+    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 5), STAGES = 2, MINB = 4, CTAS = 3, STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
 struct Tuning<6> {
-    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 6), STAGES = 2, MINB = 4, CTAS = 3, STG = 0;
+    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 6), STAGES = 2, MINB = 4, CTAS = 3, STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
 struct Tuning<7> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 7), STAGES = 2, MINB = 2, CTAS = 2, STG = 1;
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 7), STAGES = 2, MINB = 2, CTAS = 2, STG = 1, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
 struct Tuning<8> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 8), STAGES = 2, MINB = 2, CTAS = 2, STG = 1;
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 8), STAGES = 2, MINB = 2, CTAS = 2, STG = 1, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
 struct Tuning<9> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 9), STAGES = 2, MINB = 2, CTAS = 2, STG = 1;
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 9), STAGES = 2, MINB = 2, CTAS = 2, STG = 1, STG_R2C = 1, STG_C2R = 0;
 };
 
 }  // namespace kernels
