@@ -115,6 +115,7 @@ def cpu_sweep(sample_points: int, repeats: int = 1):
     from oracle import oracle_np as O
 
     lib = O.c_oracle()
+    lib.oracle_set_num_threads(os.cpu_count() or 1)  # all host threads (torchrun exports OMP_NUM_THREADS=1)
     cores = lib.oracle_num_threads()
     x = O.uniform_c64(1, sample_points).reshape(-1)
     out = np.empty_like(x)

@@ -241,18 +241,33 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
 }
 
 struct NoHook {
+    static constexpr int PASS = 0;
     SMFFT_DEV void operator()() const {}
 };
+// a callable to run once per tile, right after the first barrier that follows pass PASS (clamped to
+// the last exchange of the plan): the kernels use it to time the refill of the previous tile buffer
+template <int PASS_, class F>
+struct HookAt {
+    static constexpr int PASS = PASS_;
+    F f;
+    SMFFT_DEV void operator()() const { f(); }
+};
+template <int PASS_, class F>
+SMFFT_DEV HookAt<PASS_, F> hook_at(F f)
+{
+    return HookAt<PASS_, F>{f};
+}
 
-// hook() runs once, right after the first barrier of the transform: at that point every thread of
-// the CTA has finished ALL work of the previous tile, so the previous tile's buffer may be refilled.
+// hook() runs once per tile, right after the first barrier following pass Hook::PASS: from the first
+// barrier of a tile onwards every thread of the CTA has finished ALL work of the previous tile, so the
+// previous tile's buffer may be refilled; a later pass shortens the time the refill is in flight.
 template <class C, int PIDX, class Hook>
 SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t, const float2* tw, Hook&& hook)
 {
     fft_pass_compute<C, PIDX>(v, vt, tw);
     if constexpr (PIDX + 1 < C::P) {
         plat::sync_block();  // every thread has finished reading the previous state of the tile
-        if constexpr (PIDX == 0) hook();
+        if constexpr (PIDX == (std::remove_reference<Hook>::type::PASS < C::P - 2 ? std::remove_reference<Hook>::type::PASS : C::P - 2)) hook();
         fft_pass_scatter<C, PIDX>(v, s, fbase, vt);
         plat::sync_block();
         load_natural<C, typename C::XLayout>(v, s, fbase, t);
@@ -365,11 +380,11 @@ SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
 // In-place transform of all F transforms of the tile (XF_C2C / XF_R2C / XF_C2R).  Contract: the tile
 // is visible to the whole CTA on entry; on return the caller must synchronise before other threads
 // (or the async proxy) read the tile.
-template <class C, int XF = XF_C2C>
-SMFFT_DEV void block_fft_tile(float2* s, const float2* tw)
+template <class C, int XF = XF_C2C, class Hook = NoHook>
+SMFFT_DEV void block_fft_tile(float2* s, const float2* tw, Hook&& hook = Hook{})
 {
     float2 v[C::R];
-    block_fft_regs<C, XF>(v, s, tw, NoHook{});
+    block_fft_regs<C, XF>(v, s, tw, hook);
     const int tid = plat::tid();
     if constexpr (XF == XF_R2C) {
         r2c_tail_regs<C>(v, s, tw);

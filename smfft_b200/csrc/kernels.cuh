@@ -33,13 +33,17 @@ struct TileArgs {
 };
 
 // the per-tile transform, in place in shared memory; tile visible on entry, caller synchronises after
-template <class C, int MODE, int REPS>
-SMFFT_DEV void tile_transform(float2* s, const float2* tw)
+template <class C, int MODE, int REPS, class Hook = detail::NoHook>
+SMFFT_DEV void tile_transform(float2* s, const float2* tw, Hook&& hook = Hook{})
 {
+    if constexpr (REPS == 1) {
+        detail::block_fft_tile<C, MODE>(s, tw, hook);
+    } else {
 #pragma unroll 1
-    for (int rep = 0; rep < REPS; rep++) {
-        detail::block_fft_tile<C, MODE>(s, tw);
-        if (rep + 1 < REPS) plat::sync_block();
+        for (int rep = 0; rep < REPS; rep++) {
+            detail::block_fft_tile<C, MODE>(s, tw);
+            if (rep + 1 < REPS) plat::sync_block();
+        }
     }
 }
 
@@ -97,7 +101,8 @@ SMFFT_DEV void coop_store_tile(const float2* s, float2* __restrict__ g, long lon
     });
 }
 
-template <class C, int MODE, int IO, int STAGES, int REPS>
+// PF: the pass after which the next tile's load is issued (-1: at the top of the iteration, IO_TMA only)
+template <class C, int MODE, int IO, int STAGES, int REPS, int PF = (IO == IO_TMA ? -1 : 0)>
 SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
 {
     constexpr int TILE_BYTES = C::L * 8;
@@ -136,16 +141,21 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
         }
         if constexpr (IO == IO_TMA) {
             for (long long k = 0; k < my_tiles; k++) {
-                if (tid == 0) {
-                    const long long kn = k + STAGES - 1;  // refill the buffer tile k-1 has just left
-                    if (kn < my_tiles) {
+                // refill the buffer tile k-1 has just left, once its TMA store has finished reading it
+                auto refill = [&]() {
+                    const long long kn = k + STAGES - 1;
+                    if (tid == 0 && kn < my_tiles) {
                         if (k > 0) plat::bulk_wait_read0();
                         issue_load(kn);
                     }
-                }
+                };
+                if constexpr (PF < 0 || REPS != 1) refill();
                 plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
                 float2* s = stage_ptr(k);
-                tile_transform<C, MODE, REPS>(s, stw);
+                if constexpr (PF < 0 || REPS != 1)
+                    tile_transform<C, MODE, REPS>(s, stw);
+                else
+                    tile_transform<C, MODE, REPS>(s, stw, detail::hook_at<PF>(refill));
                 plat::fence_proxy_async();
                 plat::sync_block();
                 if (tid == 0) {
@@ -159,7 +169,7 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
             if (tid == 0) plat::bulk_wait0();
         } else {
             // results leave from registers: a tile buffer is free as soon as every thread has passed
-            // the first barrier of the NEXT tile, which is where the refill is issued (hook)
+            // the first barrier of the NEXT tile; the refill is issued there or after a later pass (PF)
             static_assert(IO != IO_TMA_STG || STAGES >= 2, "register-output staging needs two tile buffers");
             for (long long k = 0; k < my_tiles; k++) {
                 plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
@@ -168,7 +178,8 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
                     const long long kn = k + STAGES - 1;
                     if (tid == 0 && kn < my_tiles) issue_load(kn);
                 };
-                tile_transform_to_global<C, MODE, REPS>(stage_ptr(k), stw, args.gout + p0, args.n_points - p0, refill);
+                tile_transform_to_global<C, MODE, REPS>(stage_ptr(k), stw, args.gout + p0, args.n_points - p0,
+                                                        detail::hook_at<(PF < 0 ? 0 : PF)>(refill));
             }
         }
     } else {
@@ -196,13 +207,13 @@ constexpr int smem_bytes()
 }
 
 #if !defined(SMFFT_EMU)
-template <class C, int MODE, int IO, int STAGES, int REPS, int MINB>
+template <class C, int MODE, int IO, int STAGES, int REPS, int MINB, int PF = (IO == IO_TMA ? -1 : 0)>
 __global__ void __launch_bounds__(C::THREADS, MINB) smfft_tile_kernel(const __grid_constant__ TileArgs args)
 {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t a = plat::smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (a & 1023u)) & 1023u);  // SW128 needs a 1 KB aligned tile
-    tile_kernel_body<C, MODE, IO, STAGES, REPS>(args, smem);
+    tile_kernel_body<C, MODE, IO, STAGES, REPS, PF>(args, smem);
 }
 #endif
 

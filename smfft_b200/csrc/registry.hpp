@@ -13,6 +13,7 @@ struct KernelEntry {
     int tile_points, threads, smem_bytes, minb, stages;
     int ctas;    // CTAs per SM to launch (0 = occupancy limit)
     int prefer;  // 1 = the measured best staging for this size and mode
+    int pf;      // pass after which the next tile is prefetched (-1: top of the iteration)
     const void* func;
 };
 
@@ -22,7 +23,8 @@ struct EntryList {
 };
 
 // one instance with an explicit shape (used by tools/tune.cu to sweep shapes)
-template <int E, int B, int TILE_E, int STAGES, int MINB, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
+template <int E, int B, int TILE_E, int STAGES, int MINB, int MODE, int DIR, int REORDER, int IO, int TW, int REPS,
+          int PF = (IO == kernels::IO_TMA ? -1 : 0)>
 KernelEntry make_entry_shape()
 {
     using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW>;
@@ -31,7 +33,8 @@ KernelEntry make_entry_shape()
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
     k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();
     k.minb = MINB; k.stages = ST; k.ctas = 0; k.prefer = 0;
-    k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB>);
+    k.pf = PF;
+    k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB, PF>);
     return k;
 }
 
@@ -40,7 +43,8 @@ template <int E, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
 KernelEntry make_entry()
 {
     using Tn = kernels::Tuning<E>;
-    KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS>();
+    constexpr int PF = IO == kernels::IO_TMA ? Tn::PF : (Tn::PF < 0 ? 0 : Tn::PF);
+    KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS, PF>();
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
     constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
     k.prefer = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);

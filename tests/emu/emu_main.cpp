@@ -157,7 +157,7 @@ static const float2* twiddle_table()
     return g_tw.data();
 }
 
-template <int E, int B, int F, int MODE, int DIR, int REORDER, int IO, int TW, int STAGES, int REPS>
+template <int E, int B, int F, int MODE, int DIR, int REORDER, int IO, int TW, int STAGES, int REPS, int PF = (IO == kernels::IO_TMA ? -1 : 0)>
 static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, double* bank_factor)
 {
     using C = detail::BlockCfg<E, B, F, DIR, REORDER, TW>;
@@ -176,20 +176,20 @@ static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, do
     emu::BankStats st;
     if (grid <= 0 || grid > n_tiles) grid = (int)n_tiles;
     emu::launch(grid, C::THREADS, kernels::smem_bytes<C, IO, ST, MODE>(),
-                [&](unsigned char* smem) { kernels::tile_kernel_body<C, MODE, IO, ST, REPS>(args, smem); },
+                [&](unsigned char* smem) { kernels::tile_kernel_body<C, MODE, IO, ST, REPS, PF>(args, smem); },
                 bank_factor ? &st : nullptr);
     if (bank_factor) *bank_factor = st.factor();
     return 0;
 }
 
 // dispatch over (dir, reorder, io, tw) for a fixed shape
-template <int E, int B, int F, int MODE, int STAGES, int REPS>
+template <int E, int B, int F, int MODE, int STAGES, int REPS, int PFT = -1>
 static int run_shape(const float2* in, float2* out, long long n_ffts, int dir, int reorder, int io, int tw, int grid,
                      double* bf)
 {
 #define CASE(D, RO, I, T)                                                     \
     if (dir == D && reorder == RO && io == I && tw == T)                      \
-        return run_cfg<E, B, F, MODE, D, RO, I, T, STAGES, REPS>(in, out, n_ffts, grid, bf);
+        return run_cfg<E, B, F, MODE, D, RO, I, T, STAGES, REPS, (I == kernels::IO_TMA ? PFT : (PFT < 0 ? 0 : PFT))>(in, out, n_ffts, grid, bf);
     if constexpr (MODE == kernels::MODE_C2C) {
         CASE(0, 1, 0, 0) CASE(0, 0, 0, 0) CASE(1, 1, 0, 0) CASE(1, 0, 0, 0)
         CASE(0, 1, 1, 0) CASE(0, 0, 1, 0) CASE(1, 1, 1, 0) CASE(1, 0, 1, 0)
@@ -258,10 +258,10 @@ int emu_run(const void* in, void* out, int e, long long n_ffts, int mode, int di
 #define SHAPE(E)                                                                                                    \
     if (e == E) {                                                                                                   \
         using Tn = kernels::Tuning<E>;                                                                              \
-        if (mode == 0 && reps == 1) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 0 && reps == 1) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 0 && reps == 3) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 3>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
-        if (mode == 1 && reps == 1) return run_shape<E, Tn::B, Tn::F, 1, Tn::STAGES, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
-        if (mode == 2 && reps == 1) return run_shape<E, Tn::B, Tn::F, 2, Tn::STAGES, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 1 && reps == 1) return run_shape<E, Tn::B, Tn::F, 1, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 2 && reps == 1) return run_shape<E, Tn::B, Tn::F, 2, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
     }
     SHAPE(5) SHAPE(6) SHAPE(7) SHAPE(8) SHAPE(9) SHAPE(10) SHAPE(11) SHAPE(12)
 #undef SHAPE
@@ -283,6 +283,22 @@ int emu_run_alt(const void* in, void* out, int variant, long long n_ffts, int di
         case 5: return run_shape<6, 3, 16, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 64 = 8*8
         case 6: return run_shape<5, 2, 16, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 32 = 4*4*2
         case 7: return run_shape<11, 5, 1, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 2048 = 32*32*2
+    }
+    return -1;
+}
+
+// late prefetch (the refill of the previous buffer issued after pass PF instead of at the first barrier)
+int emu_run_late(const void* in, void* out, int variant, long long n_ffts, int grid)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+    switch (variant) {
+        case 0: return run_cfg<12, 4, 1, 0, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);
+        case 1: return run_cfg<12, 4, 1, 0, 1, 0, kernels::IO_TMA_STG, TW_LUT, 2, 1, 2>(i, o, n_ffts, grid, nullptr);
+        case 2: return run_cfg<10, 4, 4, 0, 0, 0, kernels::IO_TMA, TW_LUT, 2, 1, 2>(i, o, n_ffts, grid, nullptr);
+        case 3: return run_cfg<8, 4, 8, 0, 0, 1, kernels::IO_TMA_STG, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);   // P = 2: clamps to pass 0
+        case 4: return run_cfg<10, 4, 4, 1, 0, 1, kernels::IO_TMA_STG, TW_LUT, 3, 1, 1>(i, o, n_ffts, grid, nullptr);  // R2C, three buffers
+        case 5: return run_cfg<11, 4, 2, 2, 1, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);      // C2R
     }
     return -1;
 }

@@ -26,6 +26,7 @@ def emu():
     lib.emu_run.argtypes = [P, P, I, LL, I, I, I, I, I, I, I, D]
     lib.emu_run_alt.argtypes = [P, P, I, LL, I, I, I, I, I, D]
     lib.emu_run_compat.argtypes = [P, P, I, LL, I, I, I, D]
+    lib.emu_run_late.argtypes = [P, P, I, LL, I]
     return lib
 
 
@@ -186,3 +187,27 @@ def test_reference_device_api_configuration(emu, e):
     out = np.zeros_like(h)
     assert emu.emu_run_compat(h.ctypes.data, out.ctypes.data, e, 8, 2, 1, 1, None) == 0
     assert O.rel_l2(out.view(np.float32), O.c2r_packed_fp64(h)) < TOL
+
+
+@pytest.mark.parametrize("variant,e,kind", [(0, 12, "c2c_fwd_r"), (1, 12, "c2c_inv_n"), (2, 10, "c2c_fwd_n"), (3, 8, "c2c_fwd_r"),
+                                            (4, 10, "r2c"), (5, 11, "c2r")])
+def test_late_prefetch_points(emu, variant, e, kind):
+    """The next tile's load issued after a later pass (kernel parameter PF): one persistent CTA over many
+    tiles; a refill that lands in a buffer still being read shows up as wrong data in the emulator."""
+    n = 1 << e
+    nf = max(7 * 4096 // n, 7) + 1
+    if kind.startswith("c2c"):
+        x = O.uniform_c64(nf, n)
+        out = np.zeros_like(x)
+        assert emu.emu_run_late(x.ctypes.data, out.ctypes.data, variant, nf, 1) == 0
+        assert O.rel_l2(out, O.ct_c2c_fp64(x, "inv" in kind, kind.endswith("r"))) < TOL
+    elif kind == "r2c":
+        x = O.uniform_f32(nf, 2 * n)
+        out = np.zeros((nf, n), np.complex64)
+        assert emu.emu_run_late(x.ctypes.data, out.ctypes.data, variant, nf, 1) == 0
+        assert O.rel_l2(out, O.r2c_packed_fp64(x)) < TOL
+    else:
+        h = O.uniform_c64(nf, n, seed=5)
+        out = np.zeros_like(h)
+        assert emu.emu_run_late(h.ctypes.data, out.ctypes.data, variant, nf, 1) == 0
+        assert O.rel_l2(out.view(np.float32), O.c2r_packed_fp64(h)) < TOL

@@ -21,13 +21,25 @@ struct Variant {
 
 extern std::vector<Variant> g_variants;
 
-template <int E, int B, int TILE_E, int STAGES, int MINB, int IO, int REPS = 1>
+template <int E, int B, int TILE_E, int STAGES, int MINB, int IO, int REPS = 1, int PF = (IO == IO_TMA ? -1 : 0)>
 static void add_one(int hint = 0, int out_off = 0)
 {
     if constexpr (TILE_E >= E && E > B && (TILE_E - B) <= 10 && (TILE_E - B) >= 5 && !(IO == IO_TMA_STG && STAGES < 2)) {
-        g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 1, IO, TW_LUT, REPS>(), B, TILE_E, hint, out_off});
+        g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 1, IO, TW_LUT, REPS, PF>(), B, TILE_E, hint, out_off});
         if (REPS == 1 && hint == 0 && out_off == 0)
-            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 0, IO, TW_LUT, REPS>(), B, TILE_E, 0, 0});
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 0, IO, TW_LUT, REPS, PF>(), B, TILE_E, 0, 0});
+    }
+}
+
+// late-prefetch variants: more CTAs per SM at the same average load concurrency
+template <int E, int B, int TILE_E, int STAGES, int MINB, int PF>
+static void add_late(std::initializer_list<int> per_sms)
+{
+    for (int per : per_sms) {
+        const size_t before = g_variants.size();
+        add_one<E, B, TILE_E, STAGES, MINB, IO_TMA, 1, PF>();
+        add_one<E, B, TILE_E, STAGES, MINB, IO_TMA_STG, 1, PF>();
+        for (size_t i = before; i < g_variants.size(); i++) g_variants[i].per_sm = per;
     }
 }
 
@@ -47,32 +59,14 @@ static void add_shape(std::initializer_list<int> per_sms)
 template <int E>
 static void add_size()
 {
-    add_shape<E, 4, 12, 2, 2>({2});        // first: reference output for the checks; 64 KB of loads requested
-    add_shape<E, 4, 12, 2, 3>({3, 2});     // 96 / 64 KB
-    add_shape<E, 4, 12, 3, 2>({2, 1});     // 128 / 64 KB
-    add_shape<E, 4, 12, 1, 4>({4, 3});
-    add_shape<E, 4, 11, 2, 4>({4, 3});     // 64 / 48 KB
-    add_shape<E, 4, 11, 2, 6>({6, 5, 4, 3});
-    add_shape<E, 4, 11, 3, 4>({2, 3});
-    add_shape<E, 4, 10, 2, 8>({8, 6, 5});  // 64 / 48 / 40 KB
-    add_shape<E, 3, 12, 2, 2>({2});        // R = 8: 512 threads per tile, 1024 threads at 64 KB
-    add_shape<E, 3, 11, 2, 4>({4, 3});
-    add_shape<E, 3, 11, 2, 6>({6, 4});
-    add_shape<E, 3, 10, 2, 8>({8, 6});
-    add_shape<E, 5, 12, 2, 2>({2});        // R = 32
-    add_one<E, 4, 12, 1, 2, IO_LDG>();     // thread-staged comparison (no TMA)
-    g_variants.push_back(Variant{make_entry_shape<E, 4, 12, 2, 2, MODE_C2C, 0, 1, IO_TMA, TW_MUFU, 1>(), 4, 12});
-    g_variants.back().per_sm = 2;
-    if constexpr (E == 10) {
-        // staging-only ceilings (REPS = 0: tile in, tile out, no FFT)
-        for (int per : {1, 2, 3}) {
-            add_one<E, 4, 12, 2, 3, IO_TMA, 0>(); g_variants.back().per_sm = per;
-            add_one<E, 4, 12, 2, 3, IO_TMA_STG, 0>(); g_variants.back().per_sm = per;
-        }
-        for (int per : {2, 3, 4, 6}) {
-            add_one<E, 4, 11, 2, 6, IO_TMA, 0>(); g_variants.back().per_sm = per;
-            add_one<E, 4, 11, 2, 6, IO_TMA_STG, 0>(); g_variants.back().per_sm = per;
-        }
-        add_one<E, 4, 12, 3, 2, IO_TMA, 0>(); g_variants.back().per_sm = 1;
-    }
+    add_shape<E, 4, 12, 2, 2>({2});        // first: reference output for the checks; the r01 product shape (64 KB requested)
+    add_shape<E, 4, 11, 2, 4>({3});        // product shape for N <= 64
+    add_late<E, 4, 12, 2, 3, 1>({3});      // prefetch after pass 1: three CTAs
+    add_late<E, 4, 12, 2, 3, 2>({3});
+    add_late<E, 4, 12, 2, 4, 1>({4, 3});   // 64 registers: four CTAs
+    add_late<E, 4, 12, 2, 4, 2>({4});
+    add_late<E, 4, 11, 2, 6, 1>({6, 5, 4});
+    add_late<E, 4, 11, 2, 6, 2>({6});
+    add_late<E, 4, 11, 2, 8, 1>({8, 7});
+    add_late<E, 4, 10, 2, 8, 1>({12, 10, 8});
 }
