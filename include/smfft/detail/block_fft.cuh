@@ -110,14 +110,46 @@ SMFFT_DEV void fill_twiddle_table(float2* stw, const float2* __restrict__ gtw, i
 // ---- tile <-> registers ------------------------------------------------------------------------
 
 // v[m] = tile[fbase + t + m*T]  (natural "column" ownership)
+//
+// T >= 16: 16 consecutive lanes read one 128-byte row: conflict-free in SW128.
+// T < 16 (N <= 128): a half-warp spans 16/T transforms whose rows start at multiples of T, so transforms
+// f and f + 8/T see the same swizzle key (row & 7) and collide 2-way.  Those lanes instead fetch
+// register i from element i ^ 8 (offset x ^ 8T: a row of the same transform whose key differs in a
+// bit ABOVE the column bits the T lanes occupy), and the registers are swapped back with selects:
+// 2 SEL per point instead of a second shared-memory wavefront per access.
+template <class C, class LY>
+struct NaturalAccess {
+    static constexpr bool SKEW = (C::T < 16) && std::is_same<LY, LayoutSW128>::value && (C::R == 16);
+    static constexpr int D = SKEW ? 8 : 0;
+    static SMFFT_DEV int skew(int fbase)
+    {
+        if constexpr (SKEW)
+            return ((fbase >> (C::E + 3 - C::A)) & 1) * (8 * C::T);  // bit (3 - a) of the FFT index -> flip element bit 3
+        else
+            return 0;
+    }
+};
+
 template <class C, class LY = typename C::Layout>
 SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t)
 {
+    using NA = NaturalAccess<C, LY>;
     if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
         const int p0 = LY::phys(fbase + t);  // bits 4..6 do not depend on m
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
             v[m] = plat::lds64(s + p0 + m * C::T);
+        });
+    } else if constexpr (NA::SKEW) {
+        const int sk = NA::skew(fbase);
+        float2 a[C::R];
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            a[m] = plat::lds64(s + LY::phys((fbase + t + m * C::T) ^ sk));
+        });
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            v[m] = sk ? a[m ^ NA::D] : a[m];
         });
     } else {
         static_for<C::R>([&](auto M) {
@@ -130,11 +162,19 @@ SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t
 template <class C, class LY = typename C::Layout>
 SMFFT_DEV void store_natural(const float2 (&v)[C::R], float2* s, int fbase, int t)
 {
+    using NA = NaturalAccess<C, LY>;
     if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
         const int p0 = LY::phys(fbase + t);
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
             plat::sts64(s + p0 + m * C::T, v[m]);
+        });
+    } else if constexpr (NA::SKEW) {
+        const int sk = NA::skew(fbase);
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            const float2 a = sk ? v[m ^ NA::D] : v[m];
+            plat::sts64(s + LY::phys((fbase + t + m * C::T) ^ sk), a);
         });
     } else {
         static_for<C::R>([&](auto M) {

@@ -56,8 +56,7 @@ def test_c2c_all_modes(emu, e, io):
         for reorder in (1, 0):
             y, bank = run(emu, x, e, C2C, direction, reorder, io, 0)
             assert O.rel_l2(y, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL
-            if e >= 8:
-                assert bank == pytest.approx(1.0), "shared-memory accesses must be bank-conflict free for N >= 256"
+            assert bank == pytest.approx(1.0), "every shared-memory access of the C2C path must be bank-conflict free"
 
 
 @pytest.mark.parametrize("e", range(5, 13))

@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 tools/tune 29 11 > gpurun_out/tune_p.csv 2> gpurun_out/tune_p.err; echo "rc=$?"; tail -2 gpurun_out/tune_p.err; wc -l gpurun_out/tune_p.csv
+timeout 1500 tools/tune 29 11 > gpurun_out/tune_r.csv 2> gpurun_out/tune_r.err; echo "rc=$?"; tail -2 gpurun_out/tune_r.err; wc -l gpurun_out/tune_r.csv

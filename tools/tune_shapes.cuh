@@ -59,14 +59,19 @@ static void add_shape(std::initializer_list<int> per_sms)
 template <int E>
 static void add_size()
 {
-    add_shape<E, 4, 12, 2, 2>({2});        // first: reference output for the checks; the r01 product shape (64 KB requested)
-    add_shape<E, 4, 11, 2, 4>({3});        // product shape for N <= 64
-    add_late<E, 4, 12, 2, 3, 1>({3});      // prefetch after pass 1: three CTAs
-    add_late<E, 4, 12, 2, 3, 2>({3});
-    add_late<E, 4, 12, 2, 4, 1>({4, 3});   // 64 registers: four CTAs
-    add_late<E, 4, 12, 2, 4, 2>({4});
-    add_late<E, 4, 11, 2, 6, 1>({6, 5, 4});
-    add_late<E, 4, 11, 2, 6, 2>({6});
-    add_late<E, 4, 11, 2, 8, 1>({8, 7});
-    add_late<E, 4, 10, 2, 8, 1>({12, 10, 8});
+    add_shape<E, 4, 12, 2, 2>({2});        // first: reference output for the checks
+    // current product shapes
+    add_late<E, 4, 10, 2, 8, 1>({8});
+    add_late<E, 4, 11, 2, 6, 1>({5});
+    add_late<E, 4, 12, 2, 3, 1>({3});
+    // R = 32: one exchange fewer for N = 512 / 1024, cheaper last pass for 4096
+    add_shape<E, 5, 12, 2, 2>({2});
+    add_late<E, 5, 12, 2, 2, 1>({2});
+    add_late<E, 5, 12, 2, 3, 1>({3});
+    add_late<E, 5, 12, 2, 3, 2>({3});
+    add_shape<E, 5, 11, 2, 4>({4, 3});
+    add_late<E, 5, 11, 2, 4, 1>({4});
+    add_late<E, 5, 11, 2, 6, 1>({6, 5});
+    add_late<E, 5, 10, 2, 8, 1>({8, 6});
+    add_shape<E, 5, 13, 2, 1>({1});
 }
