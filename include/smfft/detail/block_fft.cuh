@@ -38,8 +38,9 @@ namespace detail {
 // Layout_  : layout of the tile on entry and exit (SW128 for the TMA kernels, linear for the
 //            reference-compatible device API);  XLayout_: layout used by the exchanges between passes.
 // VEC128_  : allow 16-byte shared accesses (needs a 16-byte aligned tile).
+// SKEW_    : de-conflict the natural accesses of small transforms (T < 16) with skewed rows + selects.
 template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128, class XLayout_ = Layout_,
-          bool VEC128_ = true>
+          bool VEC128_ = true, bool SKEW_ = true>
 struct BlockCfg {
     static constexpr int E = E_;        // log2 N
     static constexpr int N = 1 << E_;   // FFT length
@@ -56,6 +57,7 @@ struct BlockCfg {
     using Layout = Layout_;
     using XLayout = XLayout_;
     static constexpr bool VEC128 = VEC128_;
+    static constexpr bool SKEW_SMALL = SKEW_;
     static constexpr bool SAME_LAYOUT = std::is_same<Layout_, XLayout_>::value;
     static_assert(E_ > B_, "need at least two threads per FFT");
     static_assert(B_ >= 1 && B_ <= 5, "1..32 points per thread");
@@ -119,7 +121,7 @@ SMFFT_DEV void fill_twiddle_table(float2* stw, const float2* __restrict__ gtw, i
 // 2 SEL per point instead of a second shared-memory wavefront per access.
 template <class C, class LY>
 struct NaturalAccess {
-    static constexpr bool SKEW = (C::T < 16) && std::is_same<LY, LayoutSW128>::value && (C::R == 16);
+    static constexpr bool SKEW = C::SKEW_SMALL && (C::T < 16) && std::is_same<LY, LayoutSW128>::value && (C::R == 16);
     static constexpr int D = SKEW ? 8 : 0;
     static SMFFT_DEV int skew(int fbase)
     {

@@ -14,6 +14,7 @@ struct KernelEntry {
     int ctas;    // CTAs per SM to launch (0 = occupancy limit)
     int prefer;  // 1 = the measured best staging for this size and mode
     int pf;      // pass after which the next tile is prefetched (-1: top of the iteration)
+    int skew;    // small-transform bank de-conflicting on (1) / off (0)
     const void* func;
 };
 
@@ -24,16 +25,16 @@ struct EntryList {
 
 // one instance with an explicit shape (used by tools/tune.cu to sweep shapes)
 template <int E, int B, int TILE_E, int STAGES, int MINB, int MODE, int DIR, int REORDER, int IO, int TW, int REPS,
-          int PF = (IO == kernels::IO_TMA ? -1 : 0)>
+          int PF = (IO == kernels::IO_TMA ? -1 : 0), bool SKEW = true>
 KernelEntry make_entry_shape()
 {
-    using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW>;
+    using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW, detail::LayoutSW128, detail::LayoutSW128, true, SKEW>;
     constexpr int ST = IO != kernels::IO_LDG ? STAGES : 1;
     KernelEntry k;
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
     k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();
     k.minb = MINB; k.stages = ST; k.ctas = 0; k.prefer = 0;
-    k.pf = PF;
+    k.pf = PF; k.skew = SKEW;
     k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB, PF>);
     return k;
 }

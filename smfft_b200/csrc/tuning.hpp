@@ -27,17 +27,17 @@ template <int E>
 struct Tuning;
 template <>
 struct Tuning<5> {
-    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 5), STAGES = 2, MINB = 4, CTAS = 3, PF = -1;
+    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 5), STAGES = 3, MINB = 2, CTAS = 1, PF = -1;
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
 struct Tuning<6> {
-    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 6), STAGES = 2, MINB = 4, CTAS = 3, PF = -1;
-    static constexpr int STG = 1, STG_R2C = 0, STG_C2R = 0;
+    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 6), STAGES = 3, MINB = 4, CTAS = 2, PF = -1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
 struct Tuning<7> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 7), STAGES = 2, MINB = 2, CTAS = 2, PF = -1;
+    static constexpr int B = 4, TILE_E = 10, F = 1 << (TILE_E - 7), STAGES = 2, MINB = 8, CTAS = 6, PF = -1;
     static constexpr int STG = 1, STG_R2C = 0, STG_C2R = 0;
 };
 template <>

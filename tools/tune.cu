@@ -84,7 +84,7 @@ int main(int argc, char** argv)
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
 
-    printf("kind,e,n,b,tile_e,stages,minb,io,tw,reorder,reps,hint,out_off,promo,swz,pf,threads,smem,ctas_per_sm,regs,ms_med,ms_min,gbps_med,frac_of_copy,check_rel_l2\n");
+    printf("kind,e,n,b,tile_e,stages,minb,io,tw,reorder,reps,hint,out_off,promo,swz,pf,skew,threads,smem,ctas_per_sm,regs,ms_med,ms_min,gbps_med,frac_of_copy,check_rel_l2\n");
     // roofline reference: device copy of the same batch
     double copy_ms = 1e9;
     {
@@ -100,7 +100,7 @@ int main(int argc, char** argv)
         }
         std::sort(t.begin(), t.end());
         copy_ms = t[t.size() / 2];
-        printf("copy_kernel,0,0,0,0,0,0,ldg128,,,,,,,,,512,0,16,0,%.4f,%.4f,%.1f,1.000,\n", copy_ms, t[0], pts * 16.0 / copy_ms / 1e6);
+        printf("copy_kernel,0,0,0,0,0,0,ldg128,,,,,,,,,,512,0,16,0,%.4f,%.4f,%.1f,1.000,\n", copy_ms, t[0], pts * 16.0 / copy_ms / 1e6);
         t.clear();
         for (int r = 0; r < reps + 2; r++) {
             CK(cudaEventRecord(e0));
@@ -112,7 +112,7 @@ int main(int argc, char** argv)
             if (r >= 2) t.push_back(ms);
         }
         std::sort(t.begin(), t.end());
-        printf("cudaMemcpyD2D,0,0,0,0,0,0,ce,,,,,,,,,0,0,0,0,%.4f,%.4f,%.1f,%.3f,\n", t[t.size() / 2], t[0], pts * 16.0 / t[t.size() / 2] / 1e6, copy_ms / t[t.size() / 2]);
+        printf("cudaMemcpyD2D,0,0,0,0,0,0,ce,,,,,,,,,,0,0,0,0,%.4f,%.4f,%.1f,%.3f,\n", t[t.size() / 2], t[0], pts * 16.0 / t[t.size() / 2] / 1e6, copy_ms / t[t.size() / 2]);
     }
     add_all_sizes();
     const size_t CHK = 1 << 18;  // points compared between variants
@@ -184,9 +184,9 @@ int main(int argc, char** argv)
             rel = sqrt(num / den);
         }
         const double med = t[t.size() / 2];
-        printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : "fft", k.e, 1 << k.e, v.b, v.tile_e,
+        printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : "fft", k.e, 1 << k.e, v.b, v.tile_e,
                k.stages, k.minb, k.io == IO_TMA ? "tma" : (k.io == IO_LDG ? "ldg" : "tma_stg"), k.tw == TW_LUT ? "lut" : "mufu", k.reorder, k.reps, v.hint,
-               v.out_off, v.promo, v.swz, k.pf, k.threads, k.smem_bytes, per_sm, fa.numRegs, med,
+               v.out_off, v.promo, v.swz, k.pf, k.skew, k.threads, k.smem_bytes, per_sm, fa.numRegs, med,
                t[0], pts * 16.0 / med / 1e6, copy_ms / med, rel);
         fflush(stdout);
     }

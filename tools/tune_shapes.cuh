@@ -31,6 +31,18 @@ static void add_one(int hint = 0, int out_off = 0)
     }
 }
 
+// same shape without the small-N row skew (E <= 7 only)
+template <int E, int B, int TILE_E, int STAGES, int MINB, int IO>
+static void add_noskew(int per)
+{
+    if constexpr (E <= 7 && TILE_E >= E && !(IO == IO_TMA_STG && STAGES < 2)) {
+        g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 1, IO, TW_LUT, 1, (IO == IO_TMA ? -1 : 0), false>(), B, TILE_E});
+        g_variants.back().per_sm = per;
+        g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 0, IO, TW_LUT, 1, (IO == IO_TMA ? -1 : 0), false>(), B, TILE_E});
+        g_variants.back().per_sm = per;
+    }
+}
+
 // late-prefetch variants: more CTAs per SM at the same average load concurrency
 template <int E, int B, int TILE_E, int STAGES, int MINB, int PF>
 static void add_late(std::initializer_list<int> per_sms)
@@ -60,18 +72,15 @@ template <int E>
 static void add_size()
 {
     add_shape<E, 4, 12, 2, 2>({2});        // first: reference output for the checks
-    // current product shapes
-    add_late<E, 4, 10, 2, 8, 1>({8});
-    add_late<E, 4, 11, 2, 6, 1>({5});
-    add_late<E, 4, 12, 2, 3, 1>({3});
-    // R = 32: one exchange fewer for N = 512 / 1024, cheaper last pass for 4096
-    add_shape<E, 5, 12, 2, 2>({2});
-    add_late<E, 5, 12, 2, 2, 1>({2});
-    add_late<E, 5, 12, 2, 3, 1>({3});
-    add_late<E, 5, 12, 2, 3, 2>({3});
-    add_shape<E, 5, 11, 2, 4>({4, 3});
-    add_late<E, 5, 11, 2, 4, 1>({4});
-    add_late<E, 5, 11, 2, 6, 1>({6, 5});
-    add_late<E, 5, 10, 2, 8, 1>({8, 6});
-    add_shape<E, 5, 13, 2, 1>({1});
+    if constexpr (E <= 7) {
+        add_shape<E, 4, 11, 2, 4>({3});
+        add_shape<E, 4, 10, 2, 8>({6});
+        add_shape<E, 4, 11, 3, 4>({2});
+        add_shape<E, 4, 12, 3, 2>({1});
+        add_noskew<E, 4, 12, 2, 2, IO_TMA>(2); add_noskew<E, 4, 12, 2, 2, IO_TMA_STG>(2);
+        add_noskew<E, 4, 11, 2, 4, IO_TMA>(3); add_noskew<E, 4, 11, 2, 4, IO_TMA_STG>(3);
+        add_noskew<E, 4, 10, 2, 8, IO_TMA>(6); add_noskew<E, 4, 10, 2, 8, IO_TMA_STG>(6);
+        add_noskew<E, 4, 11, 3, 4, IO_TMA>(2); add_noskew<E, 4, 11, 3, 4, IO_TMA_STG>(2);
+        add_noskew<E, 4, 12, 3, 2, IO_TMA>(1); add_noskew<E, 4, 12, 3, 2, IO_TMA_STG>(1);
+    }
 }
