@@ -82,9 +82,16 @@ class ClockSampler:
                 self.p.kill()
         self.f.flush()
         self.f.seek(0)
+        text = self.f.read()
+        if not text.strip():  # the looping sampler produced nothing (very short region / busy nvidia-smi): one direct sample
+            try:
+                text = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                      capture_output=True, text=True, timeout=20).stdout
+            except Exception:
+                text = ""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
+        for line in text.splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
@@ -223,6 +230,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sm.FFT_init()
 
