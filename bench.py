@@ -299,8 +299,12 @@ def run_ours(args):
     # ---- e2e: host buffers, H2D and D2H inside the timed region, through the C ABI pipeline ----
     e2e = None
     if not args.no_e2e:
-        hx = torch.empty((BATCH_POINTS, 2), dtype=torch.float32, pin_memory=True)
-        hy = torch.empty((BATCH_POINTS, 2), dtype=torch.float32, pin_memory=True)
+        try:
+            hx = torch.empty((BATCH_POINTS, 2), dtype=torch.float32, pin_memory=True)
+            hy = torch.empty((BATCH_POINTS, 2), dtype=torch.float32, pin_memory=True)
+        except RuntimeError:  # host cannot pin 8 GiB per rank: pageable buffers (slower copies, same path)
+            hx = torch.empty((BATCH_POINTS, 2), dtype=torch.float32)
+            hy = torch.empty((BATCH_POINTS, 2), dtype=torch.float32)
         hx.copy_(x)  # same synthetic batch, now host-resident
         torch.cuda.synchronize()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))

@@ -334,3 +334,26 @@ def test_reference_host_programs_run_unmodified(prog, args):
     assert "FAILED" not in out and "Error" not in out, out
     if prog != "st":  # the Stockham program only self-checks when built with TESTING (ST/debug.h:3, ST/FFT.c:138-144)
         assert "PASSED" in out, out
+
+
+@pytest.mark.parametrize("n", [32, 256, 1024, 4096])
+def test_in_place_and_stream_and_errors(sm, n):
+    """d_output == d_input is safe (a tile is fully staged in shared memory before anything is written back);
+    launches follow torch's current stream; bad arguments come back as errors, not crashes."""
+    nf = 3 * (8192 // n) + 1
+    x = O.uniform_c64(nf, n, seed=n + 7)
+    d = to_dev(x)
+    sm.exec_c2c(d, d, n, nf, False, True)                      # in place
+    torch.cuda.synchronize()
+    assert O.rel_l2(c64(d), O.ct_c2c_fp64(x, False, True)) < TOL
+    side = torch.cuda.Stream()
+    d2, out = to_dev(x), torch.zeros_like(d)
+    with torch.cuda.stream(side):
+        sm.exec_c2c(d2, out, n, nf, True, False)
+    side.synchronize()
+    assert O.rel_l2(c64(out), O.ct_c2c_fp64(x, True, False)) < TOL
+    with pytest.raises(sm.SmfftError):
+        sm.exec_c2c(d2, out, 48, nf, False, True)              # wrong FFT length (CT:656-658)
+    with pytest.raises(sm.SmfftError):
+        sm.exec_c2c(d2.data_ptr() + 8, out, n, nf - 1, False, True)   # misaligned device pointer
+    sm.exec_c2c(d2, out, n, 0, False, True)                    # empty batch is a no-op
