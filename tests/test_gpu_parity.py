@@ -357,3 +357,13 @@ def test_in_place_and_stream_and_errors(sm, n):
     with pytest.raises(sm.SmfftError):
         sm.exec_c2c(d2.data_ptr() + 8, out, n, nf - 1, False, True)   # misaligned device pointer
     sm.exec_c2c(d2, out, n, 0, False, True)                    # empty batch is a no-op
+
+
+@pytest.mark.parametrize("argv", [["c2c", "1024", "3000", "2", "0", "1"], ["c2c", "32", "1001", "1", "1", "0"],
+                                  ["stockham", "4096", "300", "1"], ["r2c", "2048", "1500", "2"]])
+def test_cli_mirror_of_the_reference_programs(argv, capsys):
+    """python -m smfft_b200.cli: the reference's FFT.exe argument conventions, seeded data, relative-L2 verdict."""
+    from smfft_b200 import cli
+
+    assert cli.main(argv) == 0
+    assert "FFT test: PASSED" in capsys.readouterr().out
