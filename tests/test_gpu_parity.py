@@ -367,3 +367,38 @@ def test_cli_mirror_of_the_reference_programs(argv, capsys):
 
     assert cli.main(argv) == 0
     assert "FFT test: PASSED" in capsys.readouterr().out
+
+
+def test_32GiB_batch_64bit_indexing(sm):
+    """BASELINE.json configs[4]: 32 GiB on one GPU = 2^32 points, beyond the reference's 32-bit indexing
+    (SURVEY.md 0-9).  Rows sampled from the start, across the 2^31 / 2^32-byte boundaries and the very end."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 * (1 << 30):
+        pytest.skip("needs 64 GiB of free device memory")
+    pts = 1 << 32
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7)
+    x = torch.empty((pts, 2), device="cuda")
+    for i in range(8):  # generate in slices (torch.rand of 2^33 elements at once is fine too, this bounds temp memory)
+        x[i * (pts // 8):(i + 1) * (pts // 8)].uniform_(0, 1, generator=gen)
+    y = torch.empty_like(x)
+    for n, reorder in ((4096, True), (32, False), (1024, True)):
+        nf = pts // n
+        ms = sm.FFT_external_benchmark(x, y, n, nf, False, reorder)
+        torch.cuda.synchronize()
+        assert ms > 0
+        for row0 in (0, (1 << 28) // n, (1 << 31) // n - 2, (1 << 31) // n + 3, nf // 2 + 5, nf - 4):
+            xs = c64(x.view(nf, n, 2)[row0:row0 + 4])
+            ys = c64(y.view(nf, n, 2)[row0:row0 + 4])
+            assert O.rel_l2(ys, O.ct_c2c_fp64(xs, False, reorder)) < TOL, (n, row0)
+    xr = x.view(-1)
+    n = 4096
+    nf = 2 * pts // n
+    sm.exec_r2c_c2r(xr, y, n, nf, 0)
+    torch.cuda.synchronize()
+    for row0 in (0, nf // 2 + 1, nf - 3):
+        xs = xr.view(nf, n)[row0:row0 + 3].cpu().numpy()
+        ys = c64(y.view(nf, n // 2, 2)[row0:row0 + 3])
+        assert O.rel_l2(ys, O.r2c_packed_fp64(xs)) < TOL
+    del x, y
+    torch.cuda.empty_cache()
