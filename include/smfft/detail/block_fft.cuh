@@ -136,7 +136,7 @@ template <class C, class LY = typename C::Layout>
 SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t)
 {
     using NA = NaturalAccess<C, LY>;
-    if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value) {
         const int p0 = LY::phys(fbase + t);  // bits 4..6 do not depend on m
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
@@ -165,7 +165,7 @@ template <class C, class LY = typename C::Layout>
 SMFFT_DEV void store_natural(const float2 (&v)[C::R], float2* s, int fbase, int t)
 {
     using NA = NaturalAccess<C, LY>;
-    if constexpr (C::T % 128 == 0 && C::N % 128 == 0) {
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value) {
         const int p0 = LY::phys(fbase + t);
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
@@ -267,8 +267,8 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
                 const float2 lo = v[u + q * U], hi = v[u + (q + 1) * U];
                 plat::sts128(s + C::XLayout::phys(xb + q), make_float4(lo.x, lo.y, hi.x, hi.y));
             });
-        } else if constexpr (NS % 128 == 0) {
-            const int p0 = C::XLayout::phys(xb);  // q*NS leaves bits 0..6 alone
+        } else if constexpr (NS % 256 == 0) {
+            const int p0 = C::XLayout::phys(xb);  // q*NS leaves bits 0..7 alone (SW128 keys on bits 4..6, SW256 on 5..7)
             static_for<r>([&](auto QI) {
                 constexpr int q = decltype(QI)::value;
                 plat::sts64(s + p0 + q * NS, v[u + q * U]);
@@ -352,7 +352,7 @@ SMFFT_DEV float2 real_combine(float2 A, float2 B, float2 Wh)
 template <class C, int INVERSE>
 SMFFT_DEV void real_pass_regs(float2 (&v)[C::R], const float2* s, int fbase, int t, const float2* tw)
 {
-    static_assert(2 * C::R <= 32, "constant twiddles W_{2R}^m come from the W_32 table");
+    static_assert(2 * C::R <= 64, "constant twiddles W_{2R}^m come from the W_64 table");
     float2 wt;  // W_{2N}^t / 2
     if constexpr (C::TW == TW_LUT) {
         wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);

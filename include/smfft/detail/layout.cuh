@@ -20,6 +20,13 @@ struct LayoutSW128 {
     static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 4) & 7) << 1); }
 };
 
+// exchange layout for R = 32 points per thread: a thread's first-pass outputs are 32 contiguous points
+// = two 128-byte rows, so the chunk index is XORed with (row pair & 7) to keep eight consecutive
+// threads on eight different chunks
+struct LayoutSW256 {
+    static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 5) & 7) << 1); }
+};
+
 struct LayoutLinear {
     static SMFFT_HOST_DEV int phys(int x) { return x; }
 };

@@ -28,7 +28,8 @@ template <int E, int B, int TILE_E, int STAGES, int MINB, int MODE, int DIR, int
           int PF = (IO == kernels::IO_TMA ? -1 : 0), bool SKEW = true>
 KernelEntry make_entry_shape()
 {
-    using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW, detail::LayoutSW128, detail::LayoutSW128, true, SKEW>;
+    using XL = typename std::conditional<B == 5, detail::LayoutSW256, detail::LayoutSW128>::type;
+    using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW, detail::LayoutSW128, XL, true, SKEW>;
     constexpr int ST = IO != kernels::IO_LDG ? STAGES : 1;
     KernelEntry k;
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
@@ -43,7 +44,7 @@ KernelEntry make_entry_shape()
 template <int E, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
 KernelEntry make_entry()
 {
-    using Tn = kernels::Tuning<E>;
+    using Tn = typename kernels::ShapeFor<E, MODE, REORDER, REPS>::type;
     constexpr int PF = IO == kernels::IO_TMA ? Tn::PF : (Tn::PF < 0 ? 0 : Tn::PF);
     KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS, PF>();
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
@@ -72,7 +73,7 @@ EntryList build_entries()
         SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_MUFU, 1);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_MUFU, 1);
         // register-output staging (TMA in, STG out), C2C and C2R
-        if constexpr (Tuning<E>::STAGES >= 2) {
+        if constexpr (Tuning<E>::STAGES >= 2 && TuningR32<E>::STAGES >= 2) {
             SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_LUT, 1);
             SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_LUT, 1);
             SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_MUFU, 1);

@@ -19,6 +19,7 @@
 //     32 KB tile): they want more resident warps than "2 CTAs x one prefetched tile" allows, so the
 //     prefetch is issued late (after pass 1) and 3-8 smaller CTAs share the same load concurrency.
 #pragma once
+#include <type_traits>
 
 namespace smfft {
 namespace kernels {
@@ -64,6 +65,24 @@ template <>
 struct Tuning<12> {
     static constexpr int B = 4, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
     static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
+};
+
+// Natural-order transforms of 512 and 1024 points (CT reorder=1, Stockham, R2C/C2R cores) run R = 32
+// points per thread: [32,16] / [32,32] needs ONE exchange instead of two -- 39-44 SASS instructions per
+// point instead of 48-52, 48 instead of 64 bytes of shared-memory traffic per point
+// (profiles/r01_tune_radix32_r.csv: 1.286 ms vs 1.31-1.33 ms).  The no-reorder transform stays on R = 16:
+// its first read is a contiguous run per thread, which for 32 points spans two rows and conflicts 2-way.
+template <int E>
+struct TuningR32 {
+    static constexpr int B = 5, TILE_E = 12, F = 1 << (TILE_E - E), STAGES = 2, MINB = 2, CTAS = 2, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
+};
+
+// shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
+template <int E, int MODE, int REORDER, int REPS>
+struct ShapeFor {
+    static constexpr bool R32 = (E == 9 || E == 10) && REORDER == 1 && REPS == 1;
+    using type = typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type;
 };
 
 }  // namespace kernels

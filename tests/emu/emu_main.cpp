@@ -160,7 +160,8 @@ static const float2* twiddle_table()
 template <int E, int B, int F, int MODE, int DIR, int REORDER, int IO, int TW, int STAGES, int REPS, int PF = (IO == kernels::IO_TMA ? -1 : 0)>
 static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, double* bank_factor)
 {
-    using C = detail::BlockCfg<E, B, F, DIR, REORDER, TW>;
+    using XL = typename std::conditional<B == 5, detail::LayoutSW256, detail::LayoutSW128>::type;
+    using C = detail::BlockCfg<E, B, F, DIR, REORDER, TW, detail::LayoutSW128, XL>;
     constexpr int ST = IO != kernels::IO_LDG ? STAGES : 1;
     kernels::TileArgs args;
     const long long n_points = n_ffts * C::N;
@@ -258,6 +259,10 @@ int emu_run(const void* in, void* out, int e, long long n_ffts, int mode, int di
 #define SHAPE(E)                                                                                                    \
     if (e == E) {                                                                                                   \
         using Tn = kernels::Tuning<E>;                                                                              \
+        using Tq = kernels::ShapeFor<E, 0, 1, 1>::type; /* natural-order shape (R = 32 for 512 / 1024) */           \
+        if (mode == 0 && reps == 1 && reorder == 1) return run_shape<E, Tq::B, Tq::F, 0, Tq::STAGES, 1, Tq::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 1 && reps == 1) return run_shape<E, Tq::B, Tq::F, 1, Tq::STAGES, 1, Tq::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 2 && reps == 1) return run_shape<E, Tq::B, Tq::F, 2, Tq::STAGES, 1, Tq::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 0 && reps == 1) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 0 && reps == 3) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 3>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 1 && reps == 1) return run_shape<E, Tn::B, Tn::F, 1, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
@@ -312,7 +317,7 @@ int emu_alt_length(int variant)
 int emu_tile_points(int e)
 {
     switch (e) {
-#define TP(E) case E: return kernels::Tuning<E>::F << E;
+#define TP(E) case E: return kernels::TuningR32<E>::TILE_E > kernels::Tuning<E>::TILE_E ? (1 << kernels::TuningR32<E>::TILE_E) : (kernels::Tuning<E>::F << E);
         TP(5) TP(6) TP(7) TP(8) TP(9) TP(10) TP(11) TP(12)
 #undef TP
     }
