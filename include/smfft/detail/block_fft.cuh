@@ -405,18 +405,83 @@ SMFFT_DEV void block_fft_regs(float2 (&v)[C::R], float2* s, const float2* tw, Ho
     run_passes<C, 0>(v, s, fbase, vt, t, tw, hook);
 }
 
-// R2C tail: Z (registers) -> tile -> barrier -> partners read back -> X in registers
+// R2C tail, pair form.  On entry v[m] = Z[t + m*T].  Thread t evaluates the R/2 pairs (k, N-k), k = t + i*T < N/2:
+// A = Z[k] is its own register i, B = Z[N-k] belongs to thread T-t, so only the UPPER half of every thread's
+// values goes through the tile (R/2 STS + R/2 LDS per thread instead of a full write and read), and the two
+// results share H1 and W*H2:  X[k] = H1 + W H2,  X[N-k] = conj(H1 - W H2)  (RC:292-307 evaluates the same pair).
+// With s = A + conj B, d = A - conj B, Wh = W/2:  P = Wh * (d.y, -d.x);  X[k] = s/2 + P;  X[N-k] = conj(s/2 - P)
+// -- 4 adds + 8 FMA-class ops per pair.  Thread 0 has no partner for k = 0: it packs bin 0 = (X[0], X[N]) and
+// emits the self-paired bin N/2 = conj(Z[N/2]) (its own register R/2) instead.
+// On return v[i] = X[t + i*T] and v[R/2 + i] = X[r2c_hi_index(t, i)], i < R/2.
+template <class C>
+SMFFT_DEV int r2c_hi_index(int t, int i)
+{
+    return (i == 0 && t == 0) ? C::N / 2 : C::N - t - i * C::T;
+}
+// tile index (within the FFT) of register m after r2c_tail_regs
+template <class C>
+SMFFT_DEV int r2c_out_index(int t, int m)
+{
+    return m < C::R / 2 ? t + m * C::T : r2c_hi_index<C>(t, m - C::R / 2);
+}
+
 template <class C>
 SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
 {
+    static_assert(2 * C::R <= 64, "constant twiddles W_{2R}^i come from the W_64 table");
+    constexpr int H = C::R / 2;
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
-    // same layout: these are the slots this thread read in the last pass, no barrier needed before
+    // same layout: these are slots this thread read in the last pass, no barrier needed before
     if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
-    store_natural<C>(v, s, fbase, t);
+    static_for<H>([&](auto II) {
+        constexpr int m = H + decltype(II)::value;
+        plat::sts64(s + C::Layout::phys(fbase + t + m * C::T), v[m]);
+    });
+    float2 wt;  // W_{2N}^t / 2
+    if constexpr (C::TW == TW_LUT) {
+        wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
+    } else {
+        wt = tw_mufu<0, 2 * C::N>(t);
+        wt.x *= 0.5f;
+        wt.y *= 0.5f;
+    }
+    const float2 zmid = v[H];
     plat::sync_block();
-    real_pass_regs<C, 0>(v, s, fbase, t, tw);
+    static_for<H>([&](auto II) {
+        constexpr int i = decltype(II)::value;
+        const float2 Wh = mul_wconst<0, i, 2 * C::R>(wt);  // W_{2N}^{t + i T} / 2
+        const float2 A = v[i];
+        const int xb = (i == 0 && t == 0) ? fbase + C::N / 2 : fbase + C::N - t - i * C::T;
+        const float2 Bv = plat::lds64(s + C::Layout::phys(xb));
+        const float sx = A.x + Bv.x, sy = A.y - Bv.y, dx = A.x - Bv.x, dy = A.y + Bv.y;
+        const float px = Wh.x * dy + Wh.y * dx, py = Wh.y * dy - Wh.x * dx;
+        float2 lo = make_float2(0.5f * sx + px, 0.5f * sy + py);
+        float2 hi = make_float2(0.5f * sx - px, py - 0.5f * sy);
+        if constexpr (i == 0) {
+            if (t == 0) {
+                lo = make_float2(A.x + A.y, A.x - A.y);
+                hi = make_float2(zmid.x, -zmid.y);
+            }
+        }
+        v[i] = lo;
+        v[H + i] = hi;
+    });
+}
+
+// registers -> tile after the transform: natural columns, or the pair ownership left by r2c_tail_regs
+template <class C, int XF>
+SMFFT_DEV void store_result(const float2 (&v)[C::R], float2* s, int fbase, int t)
+{
+    if constexpr (XF == XF_R2C) {
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            plat::sts64(s + C::Layout::phys(fbase + r2c_out_index<C>(t, m)), v[m]);
+        });
+    } else {
+        store_natural<C>(v, s, fbase, t);
+    }
 }
 
 // In-place transform of all F transforms of the tile (XF_C2C / XF_R2C / XF_C2R).  Contract: the tile
@@ -435,7 +500,7 @@ SMFFT_DEV void block_fft_tile(float2* s, const float2* tw, Hook&& hook = Hook{})
         // with distinct entry/exchange layouts the final slots are not the ones this thread just read
         if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
     }
-    store_natural<C>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
+    store_result<C, XF>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
 }
 
 // Same transform, result written straight from registers to global memory (coalesced 8-byte
@@ -447,16 +512,21 @@ SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __r
     block_fft_regs<C, XF>(v, s, tw, hook);
     if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
     const int tid = plat::tid();
-    const int x0 = ((tid >> C::A) << C::E) + (tid & (C::T - 1));
+    const int t = tid & (C::T - 1);
+    const int fbase = (tid >> C::A) << C::E;
+    auto index = [&](auto M) {
+        constexpr int m = decltype(M)::value;
+        if constexpr (XF == XF_R2C)
+            return fbase + r2c_out_index<C>(t, m);
+        else
+            return fbase + t + m * C::T;
+    };
     if (valid >= C::L) {
-        static_for<C::R>([&](auto M) {
-            constexpr int m = decltype(M)::value;
-            plat::stg64_stream(g + x0 + m * C::T, v[m]);
-        });
+        static_for<C::R>([&](auto M) { plat::stg64_stream(g + index(M), v[decltype(M)::value]); });
     } else {
         static_for<C::R>([&](auto M) {
-            constexpr int m = decltype(M)::value;
-            if (x0 + m * C::T < valid) plat::stg64_stream(g + x0 + m * C::T, v[m]);
+            const int x = index(M);
+            if (x < valid) plat::stg64_stream(g + x, v[decltype(M)::value]);
         });
     }
 }

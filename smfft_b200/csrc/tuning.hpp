@@ -78,11 +78,58 @@ struct TuningR32 {
     static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
 };
 
+// R2C / C2R (external, REPS == 1) have their own shapes: the real pass makes them the most issue-heavy
+// kernels of the library, so they want more resident warps per byte in flight than the C2C kernels, and the
+// 512 / 1024-point cores run R = 32 (profiles/r01_tune_real_shapes.csv, sustained sweep of both kinds).
+template <int E>
+struct TuningReal;
+template <>
+struct TuningReal<5> {
+    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 5), STAGES = 2, MINB = 6, CTAS = 4, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+template <>
+struct TuningReal<6> {
+    static constexpr int B = 4, TILE_E = 10, F = 1 << (TILE_E - 6), STAGES = 2, MINB = 8, CTAS = 8, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+template <>
+struct TuningReal<7> {
+    static constexpr int B = 4, TILE_E = 10, F = 1 << (TILE_E - 7), STAGES = 2, MINB = 8, CTAS = 8, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+template <>
+struct TuningReal<8> {
+    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 8), STAGES = 2, MINB = 6, CTAS = 4, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+template <>
+struct TuningReal<9> {
+    static constexpr int B = 5, TILE_E = 11, F = 1 << (TILE_E - 9), STAGES = 2, MINB = 4, CTAS = 4, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 1;
+};
+template <>
+struct TuningReal<10> {
+    static constexpr int B = 5, TILE_E = 11, F = 1 << (TILE_E - 10), STAGES = 2, MINB = 4, CTAS = 4, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 1;
+};
+template <>
+struct TuningReal<11> {
+    static constexpr int B = 4, TILE_E = 11, F = 1, STAGES = 2, MINB = 6, CTAS = 6, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+template <>
+struct TuningReal<12> {
+    static constexpr int B = 4, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
 template <int E, int MODE, int REORDER, int REPS>
 struct ShapeFor {
-    static constexpr bool R32 = (E == 9 || E == 10) && REORDER == 1 && REPS == 1;
-    using type = typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type;
+    static constexpr bool R32 = (E == 9 || E == 10) && MODE == 0 && REORDER == 1 && REPS == 1;
+    static constexpr bool REAL = MODE != 0 && REPS == 1;
+    using type = typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type;
 };
 
 }  // namespace kernels

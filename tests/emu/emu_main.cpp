@@ -261,12 +261,11 @@ int emu_run(const void* in, void* out, int e, long long n_ffts, int mode, int di
         using Tn = kernels::Tuning<E>;                                                                              \
         using Tq = kernels::ShapeFor<E, 0, 1, 1>::type; /* natural-order shape (R = 32 for 512 / 1024) */           \
         if (mode == 0 && reps == 1 && reorder == 1) return run_shape<E, Tq::B, Tq::F, 0, Tq::STAGES, 1, Tq::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
-        if (mode == 1 && reps == 1) return run_shape<E, Tq::B, Tq::F, 1, Tq::STAGES, 1, Tq::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
-        if (mode == 2 && reps == 1) return run_shape<E, Tq::B, Tq::F, 2, Tq::STAGES, 1, Tq::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        using Tr = kernels::ShapeFor<E, 1, 1, 1>::type; /* R2C / C2R shape */                                        \
+        if (mode == 1 && reps == 1) return run_shape<E, Tr::B, Tr::F, 1, Tr::STAGES, 1, Tr::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        if (mode == 2 && reps == 1) return run_shape<E, Tr::B, Tr::F, 2, Tr::STAGES, 1, Tr::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 0 && reps == 1) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 0 && reps == 3) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 3>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
-        if (mode == 1 && reps == 1) return run_shape<E, Tn::B, Tn::F, 1, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
-        if (mode == 2 && reps == 1) return run_shape<E, Tn::B, Tn::F, 2, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
     }
     SHAPE(5) SHAPE(6) SHAPE(7) SHAPE(8) SHAPE(9) SHAPE(10) SHAPE(11) SHAPE(12)
 #undef SHAPE
@@ -317,7 +316,7 @@ int emu_alt_length(int variant)
 int emu_tile_points(int e)
 {
     switch (e) {
-#define TP(E) case E: return kernels::TuningR32<E>::TILE_E > kernels::Tuning<E>::TILE_E ? (1 << kernels::TuningR32<E>::TILE_E) : (kernels::Tuning<E>::F << E);
+#define TP(E) case E: return 1 << (kernels::TuningR32<E>::TILE_E > kernels::Tuning<E>::TILE_E ? kernels::TuningR32<E>::TILE_E : kernels::Tuning<E>::TILE_E);  // the largest product tile
         TP(5) TP(6) TP(7) TP(8) TP(9) TP(10) TP(11) TP(12)
 #undef TP
     }

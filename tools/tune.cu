@@ -1,6 +1,6 @@
 // tools/tune.cu -- shape sweep of the native kernel on one GPU (measurement tool, not product).
 //
-//   nvcc ... tools/tune.cu -o tools/tune && tools/tune [log2_points=29] [reps=5] > gpurun_out/tune.csv
+//   nvcc ... tools/tune.cu -o tools/tune && tools/tune [log2_points=29] [reps=5] [only_e=0] [real=0] > gpurun_out/tune.csv
 //
 // For every FFT size it times a list of kernel shapes (points/thread, tile size, pipeline stages,
 // CTAs/SM, TMA vs LDG staging, table vs MUFU twiddles) on a 4 GiB batch with CUDA events, checks
@@ -32,7 +32,17 @@ void add_sizes_a();
 void add_sizes_b();
 void add_sizes_c();
 void add_sizes_d();
-static void add_all_sizes() { add_sizes_a(); add_sizes_b(); add_sizes_c(); add_sizes_d(); }
+void add_sizes_real_a();
+void add_sizes_real_b();
+void add_sizes_real_c();
+static void add_all_sizes(bool real)
+{
+    if (real) {
+        add_sizes_real_a(); add_sizes_real_b(); add_sizes_real_c();
+    } else {
+        add_sizes_a(); add_sizes_b(); add_sizes_c(); add_sizes_d();
+    }
+}
 
 __global__ void copy_kernel(const float4* __restrict__ a, float4* __restrict__ b, size_t n)
 {
@@ -63,6 +73,7 @@ int main(int argc, char** argv)
     const int lg = argc > 1 ? atoi(argv[1]) : 29;
     const int reps = argc > 2 ? atoi(argv[2]) : 5;
     const int only_e = argc > 3 ? atoi(argv[3]) : 0;
+    const bool real = argc > 4 && atoi(argv[4]) != 0;  // 1: sweep the R2C / C2R shapes instead of C2C
     const long long pts = 1LL << lg;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -114,9 +125,9 @@ int main(int argc, char** argv)
         std::sort(t.begin(), t.end());
         printf("cudaMemcpyD2D,0,0,0,0,0,0,ce,,,,,,,,,,0,0,0,0,%.4f,%.4f,%.1f,%.3f,\n", t[t.size() / 2], t[0], pts * 16.0 / t[t.size() / 2] / 1e6, copy_ms / t[t.size() / 2]);
     }
-    add_all_sizes();
+    add_all_sizes(real);
     const size_t CHK = 1 << 18;  // points compared between variants
-    std::vector<float2> ref[16][3], got(CHK);
+    std::vector<float2> ref[16][5], got(CHK);
     for (const Variant& v : g_variants) {
         const KernelEntry& k = v.k;
         if (only_e && k.e != only_e) continue;
@@ -167,7 +178,7 @@ int main(int argc, char** argv)
         std::sort(t.begin(), t.end());
         CK(cudaMemcpy(got.data(), outp, CHK * 8, cudaMemcpyDeviceToHost));
         double rel = 0;
-        auto& rf = ref[k.e][k.reps == 0 ? 2 : k.reorder];
+        auto& rf = ref[k.e][k.mode != MODE_C2C ? 2 + k.mode : (k.reps == 0 ? 2 : k.reorder)];
         if (k.reps == 0 && rf.empty()) {  // staging-only variants must reproduce the input
             rf.resize(CHK);
             CK(cudaMemcpy(rf.data(), in, CHK * 8, cudaMemcpyDeviceToHost));
@@ -184,7 +195,7 @@ int main(int argc, char** argv)
             rel = sqrt(num / den);
         }
         const double med = t[t.size() / 2];
-        printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : "fft", k.e, 1 << k.e, v.b, v.tile_e,
+        printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : (k.mode == MODE_R2C ? "r2c" : k.mode == MODE_C2R ? "c2r" : "fft"), k.e, 1 << k.e, v.b, v.tile_e,
                k.stages, k.minb, k.io == IO_TMA ? "tma" : (k.io == IO_LDG ? "ldg" : "tma_stg"), k.tw == TW_LUT ? "lut" : "mufu", k.reorder, k.reps, v.hint,
                v.out_off, v.promo, v.swz, k.pf, k.skew, k.threads, k.smem_bytes, per_sm, fa.numRegs, med,
                t[0], pts * 16.0 / med / 1e6, copy_ms / med, rel);

@@ -68,19 +68,60 @@ static void add_shape(std::initializer_list<int> per_sms)
     }
 }
 
+// R2C / C2R shapes (complex core of 2^E points = real length 2^(E+1)), launched with `per` CTAs per SM
+template <int E, int B, int TILE_E, int STAGES, int MINB, int IO, int PF>
+static void add_real(std::initializer_list<int> per_sms)
+{
+    if constexpr (TILE_E >= E && E > B && (TILE_E - B) <= 10 && (TILE_E - B) >= 5) {
+        for (int per : per_sms) {
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_R2C, 0, 1, IO, TW_LUT, 1, PF>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2R, 1, 1, IO, TW_LUT, 1, PF>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+        }
+    }
+}
+
+template <int E>
+static void add_real_size()
+{
+    add_real<E, 4, 12, 2, 2, IO_TMA, -1>({2});  // first: reference output for the checks
+    add_real<E, 4, 12, 2, 2, IO_TMA_STG, 0>({2});
+    add_real<E, 4, 12, 2, 3, IO_TMA, 1>({3});
+    add_real<E, 4, 12, 2, 3, IO_TMA_STG, 1>({3});
+    add_real<E, 4, 11, 2, 6, IO_TMA, 1>({4, 5, 6});
+    add_real<E, 4, 11, 2, 6, IO_TMA_STG, 1>({4, 5, 6});
+    add_real<E, 4, 11, 2, 4, IO_TMA_STG, 0>({3, 4});
+    add_real<E, 4, 10, 2, 8, IO_TMA, 1>({6, 8});
+    add_real<E, 4, 10, 2, 8, IO_TMA_STG, 1>({6, 8});
+    add_real<E, 4, 10, 2, 8, IO_TMA_STG, 0>({6, 8});
+    if constexpr (E >= 9 && E <= 11) {
+        add_real<E, 5, 12, 2, 2, IO_TMA, 1>({2});
+        add_real<E, 5, 12, 2, 2, IO_TMA_STG, 1>({2});
+        add_real<E, 5, 12, 2, 3, IO_TMA, 1>({3});
+        add_real<E, 5, 12, 2, 3, IO_TMA_STG, 1>({3});
+        add_real<E, 5, 11, 2, 4, IO_TMA, 1>({3, 4});
+        add_real<E, 5, 11, 2, 4, IO_TMA_STG, 1>({3, 4});
+        add_real<E, 5, 11, 2, 6, IO_TMA_STG, 1>({5, 6});
+        add_real<E, 5, 11, 2, 4, IO_TMA_STG, 0>({3, 4});
+    }
+}
+
 template <int E>
 static void add_size()
 {
     add_shape<E, 4, 12, 2, 2>({2});        // first: reference output for the checks
-    if constexpr (E <= 7) {
-        add_shape<E, 4, 11, 2, 4>({3});
-        add_shape<E, 4, 10, 2, 8>({6});
-        add_shape<E, 4, 11, 3, 4>({2});
-        add_shape<E, 4, 12, 3, 2>({1});
-        add_noskew<E, 4, 12, 2, 2, IO_TMA>(2); add_noskew<E, 4, 12, 2, 2, IO_TMA_STG>(2);
-        add_noskew<E, 4, 11, 2, 4, IO_TMA>(3); add_noskew<E, 4, 11, 2, 4, IO_TMA_STG>(3);
-        add_noskew<E, 4, 10, 2, 8, IO_TMA>(6); add_noskew<E, 4, 10, 2, 8, IO_TMA_STG>(6);
-        add_noskew<E, 4, 11, 3, 4, IO_TMA>(2); add_noskew<E, 4, 11, 3, 4, IO_TMA_STG>(2);
-        add_noskew<E, 4, 12, 3, 2, IO_TMA>(1); add_noskew<E, 4, 12, 3, 2, IO_TMA_STG>(1);
+    if constexpr (E >= 9) {
+        // product R = 16 shapes
+        if constexpr (E <= 10) add_late<E, 4, 10, 2, 8, 1>({8});
+        if constexpr (E == 11) add_late<E, 4, 11, 2, 6, 1>({5, 6});
+        if constexpr (E == 12) add_late<E, 4, 12, 2, 3, 1>({3});
+        // R = 32: tile size x CTAs per SM
+        add_late<E, 5, 12, 2, 2, 1>({2});
+        add_late<E, 5, 12, 2, 3, 1>({3});
+        add_late<E, 5, 11, 2, 4, 1>({3, 4});
+        add_late<E, 5, 11, 2, 6, 1>({5, 6});
+        add_late<E, 5, 10, 2, 8, 1>({6, 8});
+        add_late<E, 5, 11, 2, 4, 0>({4});
     }
 }
