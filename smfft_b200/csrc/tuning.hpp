@@ -67,7 +67,7 @@ struct Tuning<12> {
     static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
 };
 
-// Natural-order transforms of 512 and 1024 points (CT reorder=1, Stockham, R2C/C2R cores) run R = 32
+// Natural-order transforms of 512, 1024 and 4096 points (CT reorder=1, Stockham) run R = 32
 // points per thread: [32,16] / [32,32] needs ONE exchange instead of two -- 39-44 SASS instructions per
 // point instead of 48-52, 48 instead of 64 bytes of shared-memory traffic per point
 // (profiles/r01_tune_radix32_r.csv: 1.286 ms vs 1.31-1.33 ms).  The no-reorder transform stays on R = 16:
@@ -75,7 +75,13 @@ struct Tuning<12> {
 template <int E>
 struct TuningR32 {
     static constexpr int B = 5, TILE_E = 12, F = 1 << (TILE_E - E), STAGES = 2, MINB = 2, CTAS = 2, PF = 1;
-    static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+// 4096 = [32,32,4]: still two exchanges, but 128 threads carry the tile instead of 256 (profiles/r01_tune_c2c_r32.csv)
+template <>
+struct TuningR32<12> {
+    static constexpr int B = 5, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 
 // R2C / C2R (external, REPS == 1) have their own shapes: the real pass makes them the most issue-heavy
@@ -124,10 +130,17 @@ struct TuningReal<12> {
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 
+// experiment switch (tools/ab.py): 1 = the R2C FFT_multiple instances of 512 / 1024-point cores use R = 32 as well
+#ifndef SMFFT_R32_REAL_MULTIPLE
+#define SMFFT_R32_REAL_MULTIPLE 0
+#endif
+
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
+// (compute-bound: R = 32 pays at 512 and 1024 points, 0.88 / 1.09 ms vs 1.12 / 1.13 ms, not at 4096)
 template <int E, int MODE, int REORDER, int REPS>
 struct ShapeFor {
-    static constexpr bool R32 = (E == 9 || E == 10) && MODE == 0 && REORDER == 1 && REPS == 1;
+    static constexpr bool R32 = REORDER == 1 && ((MODE == 0 && (E == 9 || E == 10 || (E == 12 && REPS == 1))) ||
+                                                 (MODE != 0 && REPS > 1 && (E == 9 || E == 10) && SMFFT_R32_REAL_MULTIPLE));
     static constexpr bool REAL = MODE != 0 && REPS == 1;
     using type = typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type;
 };

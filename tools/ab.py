@@ -21,6 +21,10 @@ def load(path):
     lib = ctypes.CDLL(path)
     lib.smfft_exec_c2c.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
                                    ctypes.c_int]
+    lib.smfft_multiple_benchmark.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
+                                             ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    lib.smfft_r2c_multiple_benchmark.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
+                                                 ctypes.POINTER(ctypes.c_double)]
     lib.smfft_exec_r2c_c2r.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int]
     assert lib.smfft_init() == 0
     return lib
@@ -58,6 +62,11 @@ def main():
         for inv in (0, 1):
             row["c2r" if inv else "r2c"] = ab(lambda: A.smfft_exec_r2c_c2r(xi, yo, 2 * n, PTS // n, inv),
                                               lambda: B.smfft_exec_r2c_c2r(xi, yo, 2 * n, PTS // n, inv))
+        ms = ctypes.c_double(0)
+        row["multiple_r1"] = ab(lambda: A.smfft_multiple_benchmark(xi, yo, n, PTS // n, 0, 1, ctypes.byref(ms)),
+                                lambda: B.smfft_multiple_benchmark(xi, yo, n, PTS // n, 0, 1, ctypes.byref(ms)), reps=7)
+        row["r2c_multiple"] = ab(lambda: A.smfft_r2c_multiple_benchmark(xi, yo, 2 * n, PTS // n, ctypes.byref(ms)),
+                                 lambda: B.smfft_r2c_multiple_benchmark(xi, yo, 2 * n, PTS // n, ctypes.byref(ms)), reps=7)
         out[n] = row
         print(n, row, flush=True)
     if len(sys.argv) > 3:

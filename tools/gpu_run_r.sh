@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "=== pytest (real transforms)"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -k "r2c or c2r or real or golden or host" 2>&1 | tail -3
-echo "=== ab new vs old R2C tail (A = new, B = old tail + R16)"; timeout 600 python tools/ab.py smfft_b200/lib/libsmfft.so smfft_b200/lib/libsmfft_nor32.so gpurun_out/ab_r2c.json 32,64,128,256,512,1024,2048,4096 2>&1 | tail -9
-echo "=== tune real"; timeout 900 tools/tune 29 5 0 1 > gpurun_out/tune_real.csv 2> gpurun_out/tune_real.err; echo "rc=$?"; wc -l gpurun_out/tune_real.csv
+echo "=== pytest"; timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -3
+echo "=== ab multiple: A = product, B = R32 multiple"; timeout 600 python tools/ab.py smfft_b200/lib/libsmfft.so smfft_b200/lib/libsmfft_r32m.so gpurun_out/ab_mult.json 512,1024,4096 2>&1 | tail -4
+echo "=== tune real e12"; timeout 900 tools/tune 29 5 12 1 > gpurun_out/tune_real_e12.csv 2> gpurun_out/tune_real_e12.err; echo "rc=$?"; cut -d, -f1-10,20,22 gpurun_out/tune_real_e12.csv | sort -t, -k12 -n | head -30

@@ -105,6 +105,11 @@ static void add_real_size()
         add_real<E, 5, 11, 2, 6, IO_TMA_STG, 1>({5, 6});
         add_real<E, 5, 11, 2, 4, IO_TMA_STG, 0>({3, 4});
     }
+    if constexpr (E == 12) {
+        add_real<E, 5, 12, 2, 3, IO_TMA, 1>({3});
+        add_real<E, 5, 12, 2, 3, IO_TMA_STG, 1>({3});
+        add_real<E, 5, 12, 2, 2, IO_TMA, 1>({2});
+    }
 }
 
 template <int E>
