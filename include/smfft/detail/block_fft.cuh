@@ -503,14 +503,12 @@ SMFFT_DEV void block_fft_tile(float2* s, const float2* tw, Hook&& hook = Hook{})
     store_result<C, XF>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
 }
 
-// Same transform, result written straight from registers to global memory (coalesced 8-byte
-// stores: consecutive threads own consecutive points).  g = start of this tile in the output.
-template <class C, int XF, class Hook>
-SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid, Hook&& hook)
+// registers -> global memory (coalesced 8-byte stores: consecutive threads own consecutive points; after the
+// R2C tail the upper half of the registers holds the descending run of the pair partners).
+// g = start of this tile in the output, valid = points of the batch left from there.
+template <class C, int XF>
+SMFFT_DEV void store_global_result(const float2 (&v)[C::R], float2* __restrict__ g, long long valid)
 {
-    float2 v[C::R];
-    block_fft_regs<C, XF>(v, s, tw, hook);
-    if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
@@ -529,6 +527,53 @@ SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __r
             if (x < valid) plat::stg64_stream(g + x, v[decltype(M)::value]);
         });
     }
+}
+
+// Same transform, result written straight from registers to global memory.
+template <class C, int XF, class Hook>
+SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid, Hook&& hook)
+{
+    float2 v[C::R];
+    block_fft_regs<C, XF>(v, s, tw, hook);
+    if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
+    store_global_result<C, XF>(v, g, valid);
+}
+
+// ---- register-direct input (kernels IO_REG): global -> registers -> passes -> global -----------------
+// Natural-order transforms only: thread t of an FFT owns x = t + m*T, so every warp-level load is one
+// contiguous run (>= 32 bytes per FFT).  The tile buffer `s` then carries only the exchanges between passes:
+// 32 instead of 64 bytes of shared-memory traffic per point for a two-pass plan.
+template <class C>
+SMFFT_DEV void load_global_natural(float2 (&v)[C::R], const float2* __restrict__ g, long long valid)
+{
+    const int tid = plat::tid();
+    const int x0 = ((tid >> C::A) << C::E) + (tid & (C::T - 1));
+    if (valid >= C::L) {
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            v[m] = plat::ldg64_stream(g + x0 + m * C::T);
+        });
+    } else {
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            v[m] = (x0 + m * C::T < valid) ? plat::ldg64_stream(g + x0 + m * C::T) : make_float2(0.0f, 0.0f);
+        });
+    }
+}
+
+// v = the thread's points of this tile (load_global_natural).  `s` may still be read by slower threads working
+// on the previous tile: the first barrier of run_passes orders that.
+template <class C, int XF>
+SMFFT_DEV void block_fft_preloaded_to_global(float2 (&v)[C::R], float2* s, const float2* tw, float2* __restrict__ g,
+                                             long long valid)
+{
+    static_assert(C::REORDER == 1 && XF != XF_C2R, "register-direct input: natural-order C2C and R2C");
+    const int tid = plat::tid();
+    const int t = tid & (C::T - 1);
+    const int fbase = (tid >> C::A) << C::E;
+    run_passes<C, 0>(v, s, fbase, t, t, tw, NoHook{});
+    if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
+    store_global_result<C, XF>(v, g, valid);
 }
 
 // ---- R2C / C2R pair pass, shared-memory form (used by include/smfft/compat.cuh, 4 points/thread) ----

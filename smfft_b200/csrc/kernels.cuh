@@ -10,6 +10,9 @@
 //            load of tile k+1 and the store of tile k-1 overlap the FFT of tile k), TMA stores.
 //   IO_LDG : same tiles staged by the threads with 16-byte LDG/STG (any 16-byte aligned pointer;
 //            also the A/B comparison for the TMA path).
+//   IO_REG : natural-order C2C / R2C without staging: each thread loads its own points from global memory
+//            into registers (the next tile's while the current one is transformed, PF >= 0), shared memory
+//            carries only the exchanges between passes, results leave from registers.
 // REPS > 1 is the FFT_multiple benchmark: the transform is re-applied in place REPS times.
 #pragma once
 #include "smfft/detail/block_fft.cuh"
@@ -18,7 +21,8 @@
 namespace smfft {
 namespace kernels {
 
-enum { IO_TMA = 0, IO_LDG = 1, IO_TMA_STG = 2 };  // TMA_STG: TMA loads, results stored from registers
+enum { IO_TMA = 0, IO_LDG = 1, IO_TMA_STG = 2, IO_REG = 3 };  // TMA_STG: TMA loads, results stored from registers
+SMFFT_CX bool io_uses_tma(int io) { return io == IO_TMA || io == IO_TMA_STG; }
 enum { MODE_C2C = detail::XF_C2C, MODE_R2C = detail::XF_R2C, MODE_C2R = detail::XF_C2R };
 
 struct TileArgs {
@@ -113,7 +117,7 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
     const long long first = plat::bid(), step = plat::nblocks();
     const long long my_tiles = first < args.n_tiles ? (args.n_tiles - first + step - 1) / step : 0;
     // compact twiddle table, once per (persistent) CTA; made visible by the first barrier below
-    constexpr int NBUF = IO != IO_LDG ? STAGES : 1;
+    constexpr int NBUF = io_uses_tma(IO) ? STAGES : 1;
     float2* stw = reinterpret_cast<float2*>(smem + NBUF * TILE_BYTES + 64);
     detail::fill_twiddle_table<C, MODE != MODE_C2C, MODE == MODE_C2R>(stw, args.tw, tid, C::THREADS);
 
@@ -182,6 +186,32 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
                                                         detail::hook_at<(PF < 0 ? 0 : PF)>(refill));
             }
         }
+    } else if constexpr (IO == IO_REG) {
+        static_assert(REPS == 1, "register-direct input is an external-benchmark path");
+        float2* s = reinterpret_cast<float2*>(smem);
+        plat::sync_block();  // twiddle table
+        auto tile_base = [&](long long k) { return (first + k * step) * C::L; };
+        if constexpr (PF < 0) {
+            for (long long k = 0; k < my_tiles; k++) {
+                const long long p0 = tile_base(k);
+                float2 v[C::R];
+                detail::load_global_natural<C>(v, args.gin + p0, args.n_points - p0);
+                detail::block_fft_preloaded_to_global<C, MODE>(v, s, stw, args.gout + p0, args.n_points - p0);
+            }
+        } else {
+            // software pipeline, unrolled by two so the register sets swap roles without moves
+            float2 a[C::R], b[C::R];
+            if (my_tiles > 0) detail::load_global_natural<C>(a, args.gin + tile_base(0), args.n_points - tile_base(0));
+            for (long long k = 0; k < my_tiles; k += 2) {
+                const long long p0 = tile_base(k), p1 = tile_base(k + 1), p2 = tile_base(k + 2);
+                if (k + 1 < my_tiles) detail::load_global_natural<C>(b, args.gin + p1, args.n_points - p1);
+                detail::block_fft_preloaded_to_global<C, MODE>(a, s, stw, args.gout + p0, args.n_points - p0);
+                if (k + 1 < my_tiles) {
+                    if (k + 2 < my_tiles) detail::load_global_natural<C>(a, args.gin + p2, args.n_points - p2);
+                    detail::block_fft_preloaded_to_global<C, MODE>(b, s, stw, args.gout + p1, args.n_points - p1);
+                }
+            }
+        }
     } else {
         float2* s = reinterpret_cast<float2*>(smem);
         plat::sync_block();
@@ -203,7 +233,7 @@ template <class C, int IO, int STAGES, int MODE = MODE_C2C>
 constexpr int smem_bytes()
 {
     constexpr int tw = C::TW == TW_LUT ? (C::TW_C2C_ENTRIES + (MODE != MODE_C2C ? C::TW_R2C_ENTRIES : 0)) * 8 : 0;
-    return (IO != IO_LDG ? STAGES : 1) * C::L * 8 + 64 + ((tw + 127) & ~127) + 1024;
+    return (io_uses_tma(IO) ? STAGES : 1) * C::L * 8 + 64 + ((tw + 127) & ~127) + 1024;
 }
 
 #if !defined(SMFFT_EMU)

@@ -30,7 +30,7 @@ KernelEntry make_entry_shape()
 {
     using XL = typename std::conditional<B == 5, detail::LayoutSW256, detail::LayoutSW128>::type;
     using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW, detail::LayoutSW128, XL, true, SKEW>;
-    constexpr int ST = IO != kernels::IO_LDG ? STAGES : 1;
+    constexpr int ST = kernels::io_uses_tma(IO) ? STAGES : 1;
     KernelEntry k;
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
     k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();

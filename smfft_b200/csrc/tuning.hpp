@@ -130,17 +130,13 @@ struct TuningReal<12> {
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 
-// experiment switch (tools/ab.py): 1 = the R2C FFT_multiple instances of 512 / 1024-point cores use R = 32 as well
-#ifndef SMFFT_R32_REAL_MULTIPLE
-#define SMFFT_R32_REAL_MULTIPLE 0
-#endif
-
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
-// (compute-bound: R = 32 pays at 512 and 1024 points, 0.88 / 1.09 ms vs 1.12 / 1.13 ms, not at 4096)
+// (compute-bound: R = 32 pays at 512 and 1024 points, C2C 0.88 / 1.09 ms vs 1.12 / 1.13 ms, R2C 1.21 / 1.23 vs
+// 1.28 / 1.27 ms, not at 4096)
 template <int E, int MODE, int REORDER, int REPS>
 struct ShapeFor {
     static constexpr bool R32 = REORDER == 1 && ((MODE == 0 && (E == 9 || E == 10 || (E == 12 && REPS == 1))) ||
-                                                 (MODE != 0 && REPS > 1 && (E == 9 || E == 10) && SMFFT_R32_REAL_MULTIPLE));
+                                                 (MODE != 0 && REPS > 1 && (E == 9 || E == 10)));
     static constexpr bool REAL = MODE != 0 && REPS == 1;
     using type = typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type;
 };

@@ -162,7 +162,7 @@ static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, do
 {
     using XL = typename std::conditional<B == 5, detail::LayoutSW256, detail::LayoutSW128>::type;
     using C = detail::BlockCfg<E, B, F, DIR, REORDER, TW, detail::LayoutSW128, XL>;
-    constexpr int ST = IO != kernels::IO_LDG ? STAGES : 1;
+    constexpr int ST = kernels::io_uses_tma(IO) ? STAGES : 1;
     kernels::TileArgs args;
     const long long n_points = n_ffts * C::N;
     const long long n_tiles = (n_points + C::L - 1) / C::L;
@@ -303,6 +303,11 @@ int emu_run_late(const void* in, void* out, int variant, long long n_ffts, int g
         case 3: return run_cfg<8, 4, 8, 0, 0, 1, kernels::IO_TMA_STG, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);   // P = 2: clamps to pass 0
         case 4: return run_cfg<10, 4, 4, 1, 0, 1, kernels::IO_TMA_STG, TW_LUT, 3, 1, 1>(i, o, n_ffts, grid, nullptr);  // R2C, three buffers
         case 5: return run_cfg<11, 4, 2, 2, 1, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);      // C2R
+        // register-direct input (IO_REG): global -> registers, with and without the software prefetch
+        case 6: return run_cfg<10, 4, 1, 0, 0, 1, kernels::IO_REG, TW_LUT, 1, 1, 0>(i, o, n_ffts, grid, nullptr);
+        case 7: return run_cfg<9, 5, 4, 0, 1, 1, kernels::IO_REG, TW_LUT, 1, 1, -1>(i, o, n_ffts, grid, nullptr);
+        case 8: return run_cfg<10, 4, 2, 1, 0, 1, kernels::IO_REG, TW_LUT, 1, 1, 0>(i, o, n_ffts, grid, nullptr);     // R2C
+        case 9: return run_cfg<7, 4, 8, 1, 0, 1, kernels::IO_REG, TW_LUT, 1, 1, -1>(i, o, n_ffts, grid, nullptr);     // R2C
     }
     return -1;
 }

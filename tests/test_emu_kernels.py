@@ -189,10 +189,12 @@ def test_reference_device_api_configuration(emu, e):
 
 
 @pytest.mark.parametrize("variant,e,kind", [(0, 12, "c2c_fwd_r"), (1, 12, "c2c_inv_n"), (2, 10, "c2c_fwd_n"), (3, 8, "c2c_fwd_r"),
-                                            (4, 10, "r2c"), (5, 11, "c2r")])
+                                            (4, 10, "r2c"), (5, 11, "c2r"),
+                                            (6, 10, "c2c_fwd_r"), (7, 9, "c2c_inv_r"), (8, 10, "r2c"), (9, 7, "r2c")])
 def test_late_prefetch_points(emu, variant, e, kind):
     """The next tile's load issued after a later pass (kernel parameter PF): one persistent CTA over many
-    tiles; a refill that lands in a buffer still being read shows up as wrong data in the emulator."""
+    tiles; a refill that lands in a buffer still being read shows up as wrong data in the emulator.
+    Variants 6-9: the register-direct input path (IO_REG, measured slower than TMA staging, kept as an experiment)."""
     n = 1 << e
     nf = max(7 * 4096 // n, 7) + 1
     if kind.startswith("c2c"):

@@ -35,9 +35,16 @@ void add_sizes_d();
 void add_sizes_real_a();
 void add_sizes_real_b();
 void add_sizes_real_c();
-static void add_all_sizes(bool real)
+void add_sizes_reg_a();
+void add_sizes_reg_b();
+void add_sizes_reg_c();
+void add_sizes_reg_d();
+void add_sizes_reg_e();
+static void add_all_sizes(int real)
 {
-    if (real) {
+    if (real == 2) {
+        add_sizes_reg_a(); add_sizes_reg_b(); add_sizes_reg_c(); add_sizes_reg_d(); add_sizes_reg_e();
+    } else if (real) {
         add_sizes_real_a(); add_sizes_real_b(); add_sizes_real_c();
     } else {
         add_sizes_a(); add_sizes_b(); add_sizes_c(); add_sizes_d();
@@ -73,7 +80,7 @@ int main(int argc, char** argv)
     const int lg = argc > 1 ? atoi(argv[1]) : 29;
     const int reps = argc > 2 ? atoi(argv[2]) : 5;
     const int only_e = argc > 3 ? atoi(argv[3]) : 0;
-    const bool real = argc > 4 && atoi(argv[4]) != 0;  // 1: sweep the R2C / C2R shapes instead of C2C
+    const int real = argc > 4 ? atoi(argv[4]) : 0;  // 1: sweep the R2C / C2R shapes instead of C2C, 2: register-direct input shapes
     const long long pts = 1LL << lg;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -140,6 +147,7 @@ int main(int argc, char** argv)
         if (per_sm < 1) continue;
         if (v.per_sm > per_sm) continue;  // shape cannot hold that many CTAs per SM
         if (v.per_sm > 0) per_sm = v.per_sm;
+        if (v.per_sm < 0) per_sm = 1 << 20;  // one CTA per tile
         TileArgs args;
         memset(&args, 0, sizeof(args));
         args.n_points = pts;
@@ -149,7 +157,7 @@ int main(int argc, char** argv)
         args.gout = outp;
         args.tw = tw;
         args.l2_hint = v.hint;
-        if (k.io != IO_LDG) {
+        if (io_uses_tma(k.io)) {
             if (encode_tile_map(&args.in_map, in, pts / 16, k.tile_points / 16, v.promo, v.swz) || encode_tile_map(&args.out_map, outp, pts / 16, k.tile_points / 16, v.promo, v.swz)) {
                 fprintf(stderr, "tensor map encode failed\n");
                 continue;
@@ -196,8 +204,8 @@ int main(int argc, char** argv)
         }
         const double med = t[t.size() / 2];
         printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : (k.mode == MODE_R2C ? "r2c" : k.mode == MODE_C2R ? "c2r" : "fft"), k.e, 1 << k.e, v.b, v.tile_e,
-               k.stages, k.minb, k.io == IO_TMA ? "tma" : (k.io == IO_LDG ? "ldg" : "tma_stg"), k.tw == TW_LUT ? "lut" : "mufu", k.reorder, k.reps, v.hint,
-               v.out_off, v.promo, v.swz, k.pf, k.skew, k.threads, k.smem_bytes, per_sm, fa.numRegs, med,
+               k.stages, k.minb, k.io == IO_TMA ? "tma" : (k.io == IO_LDG ? "ldg" : k.io == IO_REG ? "reg" : "tma_stg"), k.tw == TW_LUT ? "lut" : "mufu", k.reorder, k.reps, v.hint,
+               v.out_off, v.promo, v.swz, k.pf, k.skew, k.threads, k.smem_bytes, v.per_sm < 0 ? -1 : per_sm, fa.numRegs, med,
                t[0], pts * 16.0 / med / 1e6, copy_ms / med, rel);
         fflush(stdout);
     }

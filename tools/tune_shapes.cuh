@@ -82,6 +82,43 @@ static void add_real(std::initializer_list<int> per_sms)
     }
 }
 
+// register-direct input (IO_REG): natural-order C2C and R2C; per < 0 = one CTA per tile (non-persistent grid)
+template <int E, int B, int TILE_E, int MINB, int PF>
+static void add_reg(std::initializer_list<int> per_sms)
+{
+    if constexpr (TILE_E >= E && E > B && (TILE_E - B) <= 10 && (TILE_E - B) >= 5) {
+        for (int per : per_sms) {
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, 1, MINB, MODE_C2C, 0, 1, IO_REG, TW_LUT, 1, PF>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, 1, MINB, MODE_R2C, 0, 1, IO_REG, TW_LUT, 1, PF>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+        }
+    }
+}
+
+template <int E>
+static void add_reg_size()
+{
+    add_shape<E, 4, 12, 2, 2>({2});                 // reference outputs for the checks (C2C)
+    add_real<E, 4, 12, 2, 2, IO_TMA, -1>({2});      // (R2C / C2R)
+    add_reg<E, 4, 10, 8, -1>({8, -1});
+    add_reg<E, 4, 10, 8, 0>({4, 6, 8});
+    add_reg<E, 4, 11, 4, -1>({4, -1});
+    add_reg<E, 4, 11, 4, 0>({2, 3, 4});
+    add_reg<E, 4, 11, 6, 0>({6});
+    add_reg<E, 4, 12, 2, 0>({1, 2});
+    add_reg<E, 4, 12, 3, 0>({3});
+    add_reg<E, 4, 12, 2, -1>({2, -1});
+    if constexpr (E >= 9) {
+        add_reg<E, 5, 11, 4, -1>({4, -1});
+        add_reg<E, 5, 11, 4, 0>({2, 3, 4});
+        add_reg<E, 5, 11, 6, -1>({6, -1});
+        add_reg<E, 5, 12, 2, 0>({1, 2});
+        add_reg<E, 5, 12, 3, -1>({3, -1});
+        add_reg<E, 5, 12, 4, -1>({4, -1});
+    }
+}
+
 template <int E>
 static void add_real_size()
 {

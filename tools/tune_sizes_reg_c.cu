@@ -1,0 +1,3 @@
+// register-direct input shape instances (split so the sweep compiles in parallel)
+#include "tune_shapes.cuh"
+void add_sizes_reg_c() { add_reg_size<10>(); }
