@@ -49,15 +49,40 @@ SMFFT_DEV void stg128_stream(float2* p, float4 v)
                  "f"(v.w)
                  : "memory");
 }
+// SMFFT_LDG64_VARIANT / SMFFT_STG64_VARIANT: cache-operator experiments of tools/tune (0 = product)
+#ifndef SMFFT_LDG64_VARIANT
+#define SMFFT_LDG64_VARIANT 0
+#endif
+#ifndef SMFFT_STG64_VARIANT
+#define SMFFT_STG64_VARIANT 0
+#endif
 SMFFT_DEV float2 ldg64_stream(const float2* p)
 {
+#if SMFFT_LDG64_VARIANT == 1
+    return *p;
+#elif SMFFT_LDG64_VARIANT == 2
+    return __ldcs(p);
+#elif SMFFT_LDG64_VARIANT == 3
+    return __ldcg(p);
+#elif SMFFT_LDG64_VARIANT == 4
+    return __ldg(p);
+#else
     float2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
+#endif
 }
 SMFFT_DEV void stg64_stream(float2* p, float2 v)
 {
+#if SMFFT_STG64_VARIANT == 1
+    *p = v;
+#elif SMFFT_STG64_VARIANT == 2
+    __stcs(p, v);
+#elif SMFFT_STG64_VARIANT == 3
+    __stcg(p, v);
+#else
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#endif
 }
 
 // MUFU sin/cos (the reference's --use_fast_math twiddle path, CT/FFT-GPU-32bit.cu:18-28)

@@ -33,7 +33,7 @@ struct Tuning<5> {
 };
 template <>
 struct Tuning<6> {
-    static constexpr int B = 4, TILE_E = 11, F = 1 << (TILE_E - 6), STAGES = 3, MINB = 4, CTAS = 2, PF = -1;
+    static constexpr int B = 4, TILE_E = 10, F = 1 << (TILE_E - 6), STAGES = 2, MINB = 8, CTAS = 6, PF = 1;
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
@@ -43,8 +43,8 @@ struct Tuning<7> {
 };
 template <>
 struct Tuning<8> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 8), STAGES = 2, MINB = 2, CTAS = 2, PF = -1;
-    static constexpr int STG = 1, STG_R2C = 0, STG_C2R = 0;
+    static constexpr int B = 4, TILE_E = 10, F = 1 << (TILE_E - 8), STAGES = 2, MINB = 8, CTAS = 6, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
 struct Tuning<9> {

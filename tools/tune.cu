@@ -40,6 +40,19 @@ void add_sizes_reg_b();
 void add_sizes_reg_c();
 void add_sizes_reg_d();
 void add_sizes_reg_e();
+#ifdef TUNE_ONLY_REG_C  // cache-operator experiments: only the 1024-point register-direct shapes are linked
+void add_sizes_a() {}
+void add_sizes_b() {}
+void add_sizes_c() {}
+void add_sizes_d() {}
+void add_sizes_real_a() {}
+void add_sizes_real_b() {}
+void add_sizes_real_c() {}
+void add_sizes_reg_a() {}
+void add_sizes_reg_b() {}
+void add_sizes_reg_d() {}
+void add_sizes_reg_e() {}
+#endif
 static void add_all_sizes(int real)
 {
     if (real == 2) {

@@ -153,6 +153,16 @@ template <int E>
 static void add_size()
 {
     add_shape<E, 4, 12, 2, 2>({2});        // first: reference output for the checks
+    if constexpr (E <= 8) {
+        // product shapes of the small sizes vs the many-small-CTAs + late-prefetch shapes, sustained
+        if constexpr (E == 5) add_shape<E, 4, 12, 3, 2>({1});
+        if constexpr (E == 6) add_shape<E, 4, 11, 3, 4>({2});
+        if constexpr (E == 7) add_shape<E, 4, 10, 2, 8>({6});
+        add_late<E, 4, 12, 2, 3, 1>({3});
+        add_late<E, 4, 11, 2, 6, 1>({4, 5, 6});
+        add_late<E, 4, 10, 2, 8, 1>({6, 8});
+        add_shape<E, 4, 11, 2, 4>({3, 4});
+    }
     if constexpr (E >= 9) {
         // product R = 16 shapes
         if constexpr (E <= 10) add_late<E, 4, 10, 2, 8, 1>({8});
