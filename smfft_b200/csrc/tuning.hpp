@@ -26,9 +26,11 @@ namespace kernels {
 
 template <int E>
 struct Tuning;
+// N = 32: [TILE 12, 3 stages, 1 CTA/SM] is ~1 % faster at full clocks (1.26-1.30 ms) but has only 8 warps per SM and
+// scales with 1/clock: 1.43-1.46 ms at the 1.7 GHz a power-capped run settles at.  Six small CTAs hold 1.29 ms there.
 template <>
 struct Tuning<5> {
-    static constexpr int B = 4, TILE_E = 12, F = 1 << (TILE_E - 5), STAGES = 3, MINB = 2, CTAS = 1, PF = -1;
+    static constexpr int B = 4, TILE_E = 10, F = 1 << (TILE_E - 5), STAGES = 2, MINB = 8, CTAS = 6, PF = 1;
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 template <>
