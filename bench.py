@@ -217,6 +217,49 @@ def cufft_baseline(x, y, reps=3):
         return {"error": str(ex)[:200]}
 
 
+def other_modes(x, y, reps=5):
+    """The other BASELINE.json configurations on the same 4 GiB buffers, outside the timed region (reported only):
+    configs[2] Stockham C2C forward+inverse N = 256..4096, configs[3] R2C / C2R on 4 GiB of reals (real N = 64..8192),
+    configs[4] FFT_multiple (100 in-place repetitions per tile, compute-bound; flops = 5 N log2 N per transform).
+    ms = median of `reps` launches timed by the library's own CUDA events; GB/s from the algorithmic bytes
+    (16 B per complex point, 8 B per real point)."""
+    import math
+
+    import smfft_b200 as sm
+
+    peak, _ = measured_peak()
+
+    def med(fn):
+        fn()
+        return statistics.median([fn() for _ in range(reps)])
+
+    def row(ms, nbytes):
+        gbs = nbytes / ms / 1e6
+        return {"ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+
+    out = {"stockham_c2c": {}, "r2c": {}, "c2r": {}, "ct_multiple": {}}
+    try:
+        for n in (256, 512, 1024, 2048, 4096):
+            nf = BATCH_POINTS // n
+            out["stockham_c2c"][str(n)] = {
+                "forward": row(med(lambda: sm.Stockham_external_benchmark(x, y, n, nf, False)), BATCH_POINTS * 16),
+                "inverse": row(med(lambda: sm.Stockham_external_benchmark(x, y, n, nf, True)), BATCH_POINTS * 16)}
+        real_points = 2 * BATCH_POINTS          # the same 4 GiB read as floats
+        for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
+            nf = real_points // n
+            out["r2c"][str(n)] = row(med(lambda: sm.R2C_C2R_external_benchmark(x, y, n, nf, 0)), real_points * 8)
+            out["c2r"][str(n)] = row(med(lambda: sm.R2C_C2R_external_benchmark(x, y, n, nf, 1)), real_points * 8)
+        for n in SIZES:
+            nf = BATCH_POINTS // n              # the launcher transforms nFFTs/100 tiles' worth of data 100 times (CT:669)
+            for reorder in (1, 0):
+                ms = med(lambda: sm.FFT_multiple_benchmark(x, y, n, nf, False, bool(reorder)))
+                flops = 5.0 * n * math.log2(n) * (nf // 100) * 100
+                out["ct_multiple"][f"{n}{'r' if reorder else 'n'}"] = {"ms": round(ms, 4), "TFLOPs": round(flops / ms / 1e9, 2)}
+    except Exception as ex:  # pragma: no cover
+        out["error"] = str(ex)[:200]
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -327,7 +370,10 @@ def run_ours(args):
 
     cpu = None
     baselines = {}
+    others = None
     if rank == 0:
+        if not args.no_other_modes:
+            others = other_modes(x, y)
         if world == 1 and not args.no_cpu:
             sample = 1 << 20
             cpu_sweep(sample)
@@ -359,7 +405,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "smfft_tile_kernel (mean over the 16 instances of a step)",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": BATCH_POINTS * BYTES_PER_POINT},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "baselines": baselines,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "other_modes": others, "baselines": baselines,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -375,6 +421,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--no-other-modes", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
