@@ -39,8 +39,10 @@ namespace detail {
 //            reference-compatible device API);  XLayout_: layout used by the exchanges between passes.
 // VEC128_  : allow 16-byte shared accesses (needs a 16-byte aligned tile).
 // SKEW_    : de-conflict the natural accesses of small transforms (T < 16) with skewed rows + selects.
+// DUAL_    : 1 = one thread carries the same points of TWO transforms of the tile in the packed f32x2 lanes
+//            (block_fft_dual.cuh): half the threads, half the floating-point and exchange instructions per point.
 template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128, class XLayout_ = Layout_,
-          bool VEC128_ = true, bool SKEW_ = true>
+          bool VEC128_ = true, bool SKEW_ = true, int DUAL_ = 0>
 struct BlockCfg {
     static constexpr int E = E_;        // log2 N
     static constexpr int N = 1 << E_;   // FFT length
@@ -50,7 +52,11 @@ struct BlockCfg {
     static constexpr int T = 1 << A;    // threads per FFT
     static constexpr int F = F_;        // FFTs per tile (power of two)
     static constexpr int L = F_ * N;    // points per tile
-    static constexpr int THREADS = F_ * T;
+    static constexpr int DUAL = DUAL_;
+    static constexpr int THREADS = (F_ * T) >> DUAL_;
+    static_assert(DUAL_ == 0 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
+                                 std::is_same<Layout_, LayoutSW128>::value && VEC128_),
+                  "dual-lane transforms: an even number of transforms per tile, T >= 16, N >= 128, R >= 16, SW128 tile");
     static constexpr int DIR = DIR_;          // 0 forward (exp -), 1 inverse (exp +): FFT_Params::fft_direction
     static constexpr int REORDER = REORDER_;  // FFT_Params::fft_reorder
     static constexpr int TW = TW_;
@@ -487,20 +493,29 @@ SMFFT_DEV void store_result(const float2 (&v)[C::R], float2* s, int fbase, int t
 // In-place transform of all F transforms of the tile (XF_C2C / XF_R2C / XF_C2R).  Contract: the tile
 // is visible to the whole CTA on entry; on return the caller must synchronise before other threads
 // (or the async proxy) read the tile.
+template <class C, int XF, class Hook>
+SMFFT_DEV void dual_fft_tile(float2* s, const float2* tw, Hook&& hook);
+template <class C, int XF, class Hook>
+SMFFT_DEV void dual_fft_tile_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid, Hook&& hook);
+
 template <class C, int XF = XF_C2C, class Hook = NoHook>
 SMFFT_DEV void block_fft_tile(float2* s, const float2* tw, Hook&& hook = Hook{})
 {
-    float2 v[C::R];
-    block_fft_regs<C, XF>(v, s, tw, hook);
-    const int tid = plat::tid();
-    if constexpr (XF == XF_R2C) {
-        r2c_tail_regs<C>(v, s, tw);
-        plat::sync_block();  // every partner has been read before the packed spectrum overwrites Z
+    if constexpr (C::DUAL) {
+        dual_fft_tile<C, XF>(s, tw, hook);
     } else {
-        // with distinct entry/exchange layouts the final slots are not the ones this thread just read
-        if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+        float2 v[C::R];
+        block_fft_regs<C, XF>(v, s, tw, hook);
+        const int tid = plat::tid();
+        if constexpr (XF == XF_R2C) {
+            r2c_tail_regs<C>(v, s, tw);
+            plat::sync_block();  // every partner has been read before the packed spectrum overwrites Z
+        } else {
+            // with distinct entry/exchange layouts the final slots are not the ones this thread just read
+            if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+        }
+        store_result<C, XF>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
     }
-    store_result<C, XF>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
 }
 
 // registers -> global memory (coalesced 8-byte stores: consecutive threads own consecutive points; after the
@@ -533,10 +548,14 @@ SMFFT_DEV void store_global_result(const float2 (&v)[C::R], float2* __restrict__
 template <class C, int XF, class Hook>
 SMFFT_DEV void block_fft_tile_to_global(float2* s, const float2* tw, float2* __restrict__ g, long long valid, Hook&& hook)
 {
-    float2 v[C::R];
-    block_fft_regs<C, XF>(v, s, tw, hook);
-    if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
-    store_global_result<C, XF>(v, g, valid);
+    if constexpr (C::DUAL) {
+        dual_fft_tile_to_global<C, XF>(s, tw, g, valid, hook);
+    } else {
+        float2 v[C::R];
+        block_fft_regs<C, XF>(v, s, tw, hook);
+        if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
+        store_global_result<C, XF>(v, g, valid);
+    }
 }
 
 // ---- register-direct input (kernels IO_REG): global -> registers -> passes -> global -----------------
@@ -615,3 +634,5 @@ SMFFT_DEV void r2c_pair_pass_tile(float2* s, const float2* tw)
 
 }  // namespace detail
 }  // namespace smfft
+
+#include "block_fft_dual.cuh"

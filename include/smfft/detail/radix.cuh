@@ -4,6 +4,7 @@
 // LEN values v[OFF + i*STRIDE] (i = 0..LEN-1) by their LEN-point DFT, natural order in and out.
 // The network is a decimation-in-frequency nest with compile-time twiddles; the trailing bit
 // reversal is register renaming (every index is a compile-time constant after unrolling).
+// V is float2 (one transform) or cpair (two transforms in the packed f32x2 lanes, complex.cuh).
 // This replaces the reference's one-radix-2-stage-per-shuffle/per-barrier schedule
 // (CT/FFT-GPU-32bit.cu:363-531, ST/...:97-240) with log2(LEN) stages per register pass.
 #pragma once
@@ -12,15 +13,15 @@
 namespace smfft {
 namespace detail {
 
-template <int DIR, int LEN, int OFF, int STRIDE, int RTOT>
-SMFFT_DEV void dif_net(float2 (&v)[RTOT])
+template <int DIR, int LEN, int OFF, int STRIDE, int RTOT, class V>
+SMFFT_DEV void dif_net(V (&v)[RTOT])
 {
     if constexpr (LEN > 1) {
         constexpr int H = LEN / 2;
         static_for<H>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            const float2 a = v[OFF + i * STRIDE];
-            const float2 b = v[OFF + (i + H) * STRIDE];
+            const V a = v[OFF + i * STRIDE];
+            const V b = v[OFF + (i + H) * STRIDE];
             v[OFF + i * STRIDE] = cadd(a, b);
             v[OFF + (i + H) * STRIDE] = mul_wconst<DIR, i, LEN>(csub(a, b));
         });
@@ -29,14 +30,14 @@ SMFFT_DEV void dif_net(float2 (&v)[RTOT])
     }
 }
 
-template <int DIR, int LEN, int OFF, int STRIDE, int RTOT>
-SMFFT_DEV void dft_regs(float2 (&v)[RTOT])
+template <int DIR, int LEN, int OFF, int STRIDE, int RTOT, class V>
+SMFFT_DEV void dft_regs(V (&v)[RTOT])
 {
     static_assert(OFF + (LEN - 1) * STRIDE < RTOT, "register group out of range");
     dif_net<DIR, LEN, OFF, STRIDE, RTOT>(v);
     if constexpr (LEN > 2) {
         constexpr int LG = ilog2_c(LEN);
-        float2 t[LEN];
+        V t[LEN];
         static_for<LEN>([&](auto I) {
             constexpr int i = decltype(I)::value;
             t[i] = v[OFF + brev_c(i, LG) * STRIDE];

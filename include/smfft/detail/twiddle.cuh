@@ -44,11 +44,11 @@ SMFFT_DEV float2 tw_mufu(int m)
 
 // pw[q] = W_WN^{k q} for q = 1 .. RAD-1 (pw[0] is not written).
 // TW_LUT: `pass_tbl` is this pass's compact shared-memory table, pass_tbl[k] = W_WN^k.
-template <int DIR, int TW, int WN, int RAD>
-SMFFT_DEV void make_twiddle_powers(float2 (&pw)[RAD], int k, const float2* pass_tbl)
+template <int DIR, int TW, int WN, int RAD, class V>
+SMFFT_DEV void make_twiddle_powers(V (&pw)[RAD], int k, const float2* pass_tbl)
 {
     if constexpr (TW == TW_LUT) {
-        pw[1] = plat::lds64(pass_tbl + k);
+        pw[1] = from_scalar<V>(plat::lds64(pass_tbl + k));
         static_for<RAD>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
             if constexpr (q >= 2) {
@@ -61,7 +61,7 @@ SMFFT_DEV void make_twiddle_powers(float2 (&pw)[RAD], int k, const float2* pass_
     } else {
         static_for<RAD>([&](auto Q) {
             constexpr int q = decltype(Q)::value;
-            if constexpr (q >= 1) pw[q] = tw_mufu<DIR, WN>(k * q);
+            if constexpr (q >= 1) pw[q] = from_scalar<V>(tw_mufu<DIR, WN>(k * q));
         });
     }
 }

@@ -15,6 +15,7 @@ struct KernelEntry {
     int prefer;  // 1 = the measured best staging for this size and mode
     int pf;      // pass after which the next tile is prefetched (-1: top of the iteration)
     int skew;    // small-transform bank de-conflicting on (1) / off (0)
+    int dual;    // 1 = two transforms per thread in the packed f32x2 lanes (block_fft_dual.cuh)
     const void* func;
 };
 
@@ -25,17 +26,17 @@ struct EntryList {
 
 // one instance with an explicit shape (used by tools/tune.cu to sweep shapes)
 template <int E, int B, int TILE_E, int STAGES, int MINB, int MODE, int DIR, int REORDER, int IO, int TW, int REPS,
-          int PF = (IO == kernels::IO_TMA ? -1 : 0), bool SKEW = true>
+          int PF = (IO == kernels::IO_TMA ? -1 : 0), bool SKEW = true, int DUAL = 0>
 KernelEntry make_entry_shape()
 {
     using XL = typename std::conditional<B == 5, detail::LayoutSW256, detail::LayoutSW128>::type;
-    using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW, detail::LayoutSW128, XL, true, SKEW>;
+    using C = detail::BlockCfg<E, B, (1 << (TILE_E - E)), DIR, REORDER, TW, detail::LayoutSW128, XL, true, SKEW, DUAL>;
     constexpr int ST = kernels::io_uses_tma(IO) ? STAGES : 1;
     KernelEntry k;
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
     k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();
     k.minb = MINB; k.stages = ST; k.ctas = 0; k.prefer = 0;
-    k.pf = PF; k.skew = SKEW;
+    k.pf = PF; k.skew = SKEW; k.dual = DUAL;
     k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB, PF>);
     return k;
 }

@@ -27,6 +27,7 @@ def emu():
     lib.emu_run_alt.argtypes = [P, P, I, LL, I, I, I, I, I, D]
     lib.emu_run_compat.argtypes = [P, P, I, LL, I, I, I, D]
     lib.emu_run_late.argtypes = [P, P, I, LL, I]
+    lib.emu_run_dual.argtypes = [P, P, I, I, LL, I, I, I, I, I, D]
     return lib
 
 
@@ -212,3 +213,91 @@ def test_late_prefetch_points(emu, variant, e, kind):
         out = np.zeros_like(h)
         assert emu.emu_run_late(h.ctypes.data, out.ctypes.data, variant, nf, 1) == 0
         assert O.rel_l2(out.view(np.float32), O.c2r_packed_fp64(h)) < TOL
+
+
+DUAL_SHAPES = [(8, 4), (9, 4), (10, 4), (11, 4), (12, 4), (9, 5), (10, 5), (11, 5)]
+IO_NAMES = {IO_TMA: "tma", IO_LDG: "ldg", IO_TMA_STG: "tma_stg"}
+
+
+def run_dual(lib, x, out, e, b, kind, io, tw=0, reps=1, grid=2, want_bank=True):
+    bank = ctypes.c_double(0)
+    n_ffts = x.size // (1 << e) if x.dtype == np.complex64 else x.size // (2 << e)
+    rc = lib.emu_run_dual(x.ctypes.data, out.ctypes.data, e, b, n_ffts, kind, io, tw, reps, grid,
+                          ctypes.byref(bank) if want_bank else None)
+    assert rc == 0, f"dual configuration not instantiated: e={e} b={b} kind={kind} io={io} tw={tw} reps={reps}"
+    return bank.value
+
+
+@pytest.mark.parametrize("e,b", DUAL_SHAPES)
+def test_dual_lane_c2c(emu, e, b):
+    """block_fft_dual.cuh: two transforms per thread in the packed f32x2 lanes (cpair), chunk exchange layout.
+    Odd transform counts leave lane 1 of the last pair on TMA zero fill / LDG guards."""
+    n = 1 << e
+    nf = max(4096 // n, 2) + 1   # one full tile and a ragged one with an odd transform count
+    x = O.uniform_c64(nf, n)
+    for kind, (direction, reorder) in enumerate(((0, 1), (1, 0), (0, 0), (1, 1))):
+        ref = O.ct_c2c_fp64(x, bool(direction), bool(reorder))
+        for io in (IO_TMA, IO_TMA_STG, IO_LDG):
+            if (kind, io) in ((2, IO_TMA_STG), (3, IO_TMA_STG), (1, IO_LDG), (3, IO_LDG)):
+                continue  # not instantiated in the emulator
+            out = np.zeros_like(x)
+            bank = run_dual(emu, x, out, e, b, kind, io, grid=1 if io == IO_TMA_STG else 2)
+            assert O.rel_l2(out, ref) < TOL, (kind, IO_NAMES[io])
+            if b == 4 or reorder == 1:  # R = 32: the contiguous first read of the no-reorder transform spans two rows (2-way)
+                assert bank == pytest.approx(1.0), f"dual C2C accesses must be bank-conflict free ({kind}, {IO_NAMES[io]}): {bank}"
+    out = np.zeros_like(x)
+    run_dual(emu, x, out, e, b, 0, IO_TMA, tw=1)
+    assert O.rel_l2(out, O.ct_c2c_fp64(x, False, True)) < TOL
+
+
+@pytest.mark.parametrize("e,b", DUAL_SHAPES)
+def test_dual_lane_r2c_c2r(emu, e, b):
+    n = 2 << e
+    nf = max(4096 // (n // 2), 2) + 1
+    x = O.uniform_f32(nf, n)
+    h = O.uniform_c64(nf, n // 2, seed=5)
+    for io in (IO_TMA, IO_TMA_STG, IO_LDG):
+        y = np.zeros((nf, n // 2), np.complex64)
+        bank = run_dual(emu, x, y, e, b, 4, io, grid=1 if io == IO_TMA_STG else 2)
+        assert O.rel_l2(y, O.r2c_packed_fp64(x)) < TOL, IO_NAMES[io]
+        assert bank < 1.2, f"R2C: only the descending partner / mirror runs may conflict ({bank})"
+        z = np.zeros_like(h)
+        run_dual(emu, h, z, e, b, 5, io, grid=1 if io == IO_TMA_STG else 2)
+        assert O.rel_l2(z.view(np.float32), O.c2r_packed_fp64(h)) < TOL, IO_NAMES[io]
+    y = np.zeros((nf, n // 2), np.complex64)
+    run_dual(emu, x, y, e, b, 4, IO_TMA, tw=1)
+    assert O.rel_l2(y, O.r2c_packed_fp64(x)) < TOL
+    z = np.zeros_like(h)
+    run_dual(emu, h, z, e, b, 5, IO_LDG, tw=1)
+    assert O.rel_l2(z.view(np.float32), O.c2r_packed_fp64(h)) < TOL
+
+
+@pytest.mark.parametrize("e,b", [(8, 4), (10, 4), (11, 4), (10, 5)])
+def test_dual_lane_multiple_and_one_hot(emu, e, b):
+    n = 1 << e
+    x = (O.uniform_c64(5, n) / np.float32(n)).astype(np.complex64)
+    y = np.zeros_like(x)
+    run_dual(emu, x, y, e, b, 0, IO_LDG, reps=3)
+    assert O.rel_l2(y, np.fft.fft(np.fft.fft(np.fft.fft(x.astype(np.complex128))))) < TOL
+    ref0 = x.astype(np.complex128)
+    for _ in range(3):
+        ref0 = O.ct_c2c_fp64(ref0, False, False)
+    y0 = np.zeros_like(x)
+    run_dual(emu, x, y0, e, b, 2, IO_LDG, reps=3)
+    assert O.rel_l2(y0, ref0) < TOL
+    xr = (O.uniform_f32(5, 2 * n) / np.float32(n)).astype(np.float32)
+    yr = np.zeros((5, n), np.complex64)
+    run_dual(emu, xr, yr, e, b, 4, IO_LDG, reps=3)  # R2C re-applied to its own packed output, as the kernel does
+    cur = xr
+    for _ in range(3):
+        cur = O.r2c_packed_fp64(cur.astype(np.float32) if cur.dtype != np.float32 else cur).astype(np.complex64).view(np.float32)
+    assert O.rel_l2(yr, cur.view(np.complex64)) < 1e-4
+    # exact permutation of the no-reorder transform, both lanes: delta_p -> W^{brev(p) k}
+    perm = O.c_reorder_index(n)
+    ps = np.unique(np.concatenate([np.arange(min(n, 40)), np.random.default_rng(e).integers(0, n, 9), [n - 1]]))
+    oh = np.zeros((len(ps), n), np.complex64)
+    oh[np.arange(len(ps)), ps] = 1
+    out = np.zeros_like(oh)
+    run_dual(emu, oh, out, e, b, 2, IO_TMA)
+    for row, p in enumerate(ps):
+        assert int(np.rint((-np.angle(out[row, 1]) * n / (2 * np.pi)))) % n == perm[p]
