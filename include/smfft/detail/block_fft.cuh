@@ -39,7 +39,8 @@ namespace detail {
 //            reference-compatible device API);  XLayout_: layout used by the exchanges between passes.
 // VEC128_  : allow 16-byte shared accesses (needs a 16-byte aligned tile).
 // SKEW_    : de-conflict the natural accesses of small transforms (T < 16) with skewed rows + selects.
-// DUAL_    : 1 = one thread carries the same points of TWO transforms of the tile in the packed f32x2 lanes
+// DUAL_    : 2 = packed f32x2 add / subtract on (re, im) in the butterflies (same threads, fewer issue slots);
+//            1 = one thread carries the same points of TWO transforms of the tile in the packed f32x2 lanes
 //            (block_fft_dual.cuh): half the threads, half the floating-point and exchange instructions per point.
 template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128, class XLayout_ = Layout_,
           bool VEC128_ = true, bool SKEW_ = true, int DUAL_ = 0>
@@ -52,9 +53,10 @@ struct BlockCfg {
     static constexpr int T = 1 << A;    // threads per FFT
     static constexpr int F = F_;        // FFTs per tile (power of two)
     static constexpr int L = F_ * N;    // points per tile
-    static constexpr int DUAL = DUAL_;
-    static constexpr int THREADS = (F_ * T) >> DUAL_;
-    static_assert(DUAL_ == 0 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
+    static constexpr int DUAL = DUAL_ == 1;
+    static constexpr int PACK = DUAL_ == 2;  // one transform per thread, packed (re, im) add / subtract in the butterflies
+    static constexpr int THREADS = (F_ * T) >> DUAL;
+    static_assert(DUAL_ == 0 || DUAL_ == 2 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
                                  std::is_same<Layout_, LayoutSW128>::value && VEC128_),
                   "dual-lane transforms: an even number of transforms per tile, T >= 16, N >= 128, R >= 16, SW128 tile");
     static constexpr int DIR = DIR_;          // 0 forward (exp -), 1 inverse (exp +): FFT_Params::fft_direction
@@ -253,7 +255,7 @@ SMFFT_DEV void fft_pass_compute(float2 (&v)[C::R], int vt, const float2* tw)
     }
     static_for<U>([&](auto UI) {
         constexpr int u = decltype(UI)::value;
-        dft_regs<C::DIR, r, u, U, C::R>(v);
+        dft_regs<C::PACK, C::DIR, r, u, U, C::R>(v);
     });
 }
 

@@ -122,7 +122,7 @@ SMFFT_DEV void dual_pass_compute(cpair (&v)[C::R], int vt, const float2* tw)
     }
     static_for<U>([&](auto UI) {
         constexpr int u = decltype(UI)::value;
-        dft_regs<C::DIR, r, u, U, C::R>(v);
+        dft_regs<0, C::DIR, r, u, U, C::R>(v);
     });
 }
 

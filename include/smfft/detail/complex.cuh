@@ -19,13 +19,8 @@ SMFFT_DEV void static_for(F&& f)
     static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
 }
 
-#if defined(SMFFT_PACKED_F32X2) && !defined(SMFFT_EMU)
-SMFFT_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
-SMFFT_DEV float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
-#else
 SMFFT_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SMFFT_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-#endif
 SMFFT_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 SMFFT_DEV float2 csqr(float2 a) { return make_float2(a.x * a.x - a.y * a.y, 2.0f * a.x * a.y); }
 
@@ -59,6 +54,17 @@ SMFFT_DEV float2 neg(float2 a) { return make_float2(-a.x, -a.y); }  // folds int
 SMFFT_DEV float2 sub(float2 a, float2 b) { return add(a, neg(b)); }
 SMFFT_DEV float2 bc(float c) { return make_float2(c, c); }
 }  // namespace pk
+// one complex value, (re, im) in the two lanes: add / subtract as ONE packed instruction (BlockCfg::PACK kernels)
+template <int PACK>
+SMFFT_DEV float2 cadd_p(float2 a, float2 b)
+{
+    if constexpr (PACK) return pk::add(a, b); else return make_float2(a.x + b.x, a.y + b.y);
+}
+template <int PACK>
+SMFFT_DEV float2 csub_p(float2 a, float2 b)
+{
+    if constexpr (PACK) return pk::sub(a, b); else return make_float2(a.x - b.x, a.y - b.y);
+}
 SMFFT_DEV cpair cadd(cpair a, cpair b) { return cpair{pk::add(a.re, b.re), pk::add(a.im, b.im)}; }
 SMFFT_DEV cpair csub(cpair a, cpair b) { return cpair{pk::sub(a.re, b.re), pk::sub(a.im, b.im)}; }
 SMFFT_DEV cpair cmul(cpair a, cpair b)
@@ -73,6 +79,10 @@ SMFFT_DEV cpair csqr(cpair a)
 // the same complex value in both lanes
 SMFFT_DEV cpair cdup(float2 w) { return cpair{pk::bc(w.x), pk::bc(w.y)}; }
 // value-type dispatch for code shared by the scalar and the packed paths
+template <int PACK>
+SMFFT_DEV cpair cadd_p(cpair a, cpair b) { return cadd(a, b); }
+template <int PACK>
+SMFFT_DEV cpair csub_p(cpair a, cpair b) { return csub(a, b); }
 template <class V>
 SMFFT_DEV V from_scalar(float2 w);
 template <>

@@ -36,7 +36,7 @@ KernelEntry make_entry_shape()
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
     k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();
     k.minb = MINB; k.stages = ST; k.ctas = 0; k.prefer = 0;
-    k.pf = PF; k.skew = SKEW; k.dual = DUAL;
+    k.pf = PF; k.skew = SKEW; k.dual = DUAL;  // 0 scalar, 1 dual-lane, 2 packed add / subtract
     k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB, PF>);
     return k;
 }
@@ -47,7 +47,8 @@ KernelEntry make_entry()
 {
     using Tn = typename kernels::ShapeFor<E, MODE, REORDER, REPS>::type;
     constexpr int PF = IO == kernels::IO_TMA ? Tn::PF : (Tn::PF < 0 ? 0 : Tn::PF);
-    KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS, PF>();
+    constexpr int ARITH = kernels::ArithFor<E, MODE, REORDER, REPS>::value;
+    KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS, PF, true, ARITH>();
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
     constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
     k.prefer = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);

@@ -132,6 +132,27 @@ struct TuningReal<12> {
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 
+// arithmetic flavour of one kernel instance (BlockCfg::DUAL_): 0 = scalar, 1 = dual-lane, 2 = packed (re, im) add / subtract
+// in the butterflies.  Packed add / subtract removes ~9 % of the issue slots; it pays where a kernel is issue-bound
+// (interleaved A/B against the all-scalar build, profiles/r01_ab_scalar_vs_product.json and ..._vs_packed_all.json:
+// C2R -1.4..-7.7 % at every size, R2C of 4096 / 8192 reals -4..-6 %, FFT_multiple -2..-11 %) and is neutral or slightly
+// negative (+-1 %) for the HBM-bound C2C external kernels and the other R2C sizes, which stay scalar; the R = 32 R2C
+// FFT_multiple shapes (512 / 1024 points) lose 1-3 % and stay scalar too.
+// The dual-lane form (block_fft_dual.cuh: two transforms per thread, ALL arithmetic and exchanges packed, half the
+// instructions per point) is NOT used by the product: it also halves the resident warps, and the large and real
+// kernels turn out to be bound by shared-memory wavefronts and latency, not by issue slots alone
+// (profiles/r01_tune_dual_a.csv: equal at 2048 points, 3-12 % slower elsewhere).  It stays as a measured experiment
+// with emulator coverage (tools/tune_dual, tests/test_emu_kernels.py).
+template <int E, int MODE, int REORDER, int REPS>
+struct ArithFor {
+#if defined(SMFFT_FORCE_ARITH)
+    static constexpr int value = SMFFT_FORCE_ARITH;
+#else
+    static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : 2)
+                                 : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2 : 0;
+#endif
+};
+
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
 // (compute-bound: R = 32 pays at 512 and 1024 points, C2C 0.88 / 1.09 ms vs 1.12 / 1.13 ms, R2C 1.21 / 1.23 vs
 // 1.28 / 1.27 ms, not at 4096)

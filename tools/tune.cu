@@ -40,6 +40,11 @@ void add_sizes_reg_b();
 void add_sizes_reg_c();
 void add_sizes_reg_d();
 void add_sizes_reg_e();
+void add_sizes_dual_a();
+void add_sizes_dual_b();
+void add_sizes_dual_c();
+void add_sizes_dual_d();
+void add_sizes_dual_e();
 #ifdef TUNE_ONLY_REG_C  // cache-operator experiments: only the 1024-point register-direct shapes are linked
 void add_sizes_a() {}
 void add_sizes_b() {}
@@ -53,9 +58,25 @@ void add_sizes_reg_b() {}
 void add_sizes_reg_d() {}
 void add_sizes_reg_e() {}
 #endif
+#ifdef TUNE_ONLY_DUAL  // only the dual-lane sweep is linked
+void add_sizes_a() {}
+void add_sizes_b() {}
+void add_sizes_c() {}
+void add_sizes_d() {}
+void add_sizes_real_a() {}
+void add_sizes_real_b() {}
+void add_sizes_real_c() {}
+void add_sizes_reg_a() {}
+void add_sizes_reg_b() {}
+void add_sizes_reg_c() {}
+void add_sizes_reg_d() {}
+void add_sizes_reg_e() {}
+#endif
 static void add_all_sizes(int real)
 {
-    if (real == 2) {
+    if (real == 3) {
+        add_sizes_dual_a(); add_sizes_dual_b(); add_sizes_dual_c(); add_sizes_dual_d(); add_sizes_dual_e();
+    } else if (real == 2) {
         add_sizes_reg_a(); add_sizes_reg_b(); add_sizes_reg_c(); add_sizes_reg_d(); add_sizes_reg_e();
     } else if (real) {
         add_sizes_real_a(); add_sizes_real_b(); add_sizes_real_c();
@@ -115,7 +136,7 @@ int main(int argc, char** argv)
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
 
-    printf("kind,e,n,b,tile_e,stages,minb,io,tw,reorder,reps,hint,out_off,promo,swz,pf,skew,threads,smem,ctas_per_sm,regs,ms_med,ms_min,gbps_med,frac_of_copy,check_rel_l2\n");
+    printf("kind,e,n,b,tile_e,stages,minb,io,tw,reorder,reps,hint,out_off,promo,swz,pf,skew,dual,threads,smem,ctas_per_sm,regs,ms_med,ms_min,gbps_med,frac_of_copy,check_rel_l2\n");
     // roofline reference: device copy of the same batch
     double copy_ms = 1e9;
     {
@@ -131,7 +152,7 @@ int main(int argc, char** argv)
         }
         std::sort(t.begin(), t.end());
         copy_ms = t[t.size() / 2];
-        printf("copy_kernel,0,0,0,0,0,0,ldg128,,,,,,,,,,512,0,16,0,%.4f,%.4f,%.1f,1.000,\n", copy_ms, t[0], pts * 16.0 / copy_ms / 1e6);
+        printf("copy_kernel,0,0,0,0,0,0,ldg128,,,,,,,,,,,512,0,16,0,%.4f,%.4f,%.1f,1.000,\n", copy_ms, t[0], pts * 16.0 / copy_ms / 1e6);
         t.clear();
         for (int r = 0; r < reps + 2; r++) {
             CK(cudaEventRecord(e0));
@@ -143,11 +164,11 @@ int main(int argc, char** argv)
             if (r >= 2) t.push_back(ms);
         }
         std::sort(t.begin(), t.end());
-        printf("cudaMemcpyD2D,0,0,0,0,0,0,ce,,,,,,,,,,0,0,0,0,%.4f,%.4f,%.1f,%.3f,\n", t[t.size() / 2], t[0], pts * 16.0 / t[t.size() / 2] / 1e6, copy_ms / t[t.size() / 2]);
+        printf("cudaMemcpyD2D,0,0,0,0,0,0,ce,,,,,,,,,,,0,0,0,0,%.4f,%.4f,%.1f,%.3f,\n", t[t.size() / 2], t[0], pts * 16.0 / t[t.size() / 2] / 1e6, copy_ms / t[t.size() / 2]);
     }
     add_all_sizes(real);
     const size_t CHK = 1 << 18;  // points compared between variants
-    std::vector<float2> ref[16][5], got(CHK);
+    std::vector<float2> ref[16][8], got(CHK);
     for (const Variant& v : g_variants) {
         const KernelEntry& k = v.k;
         if (only_e && k.e != only_e) continue;
@@ -163,8 +184,10 @@ int main(int argc, char** argv)
         if (v.per_sm < 0) per_sm = 1 << 20;  // one CTA per tile
         TileArgs args;
         memset(&args, 0, sizeof(args));
-        args.n_points = pts;
-        args.n_tiles = pts / k.tile_points;
+        // FFT_multiple variants (reps > 1): 1/128 of the batch, transformed reps times in place (CT:669 uses 1/100)
+        const long long run_pts = k.reps > 1 ? (pts / 128) / k.tile_points * k.tile_points : pts;
+        args.n_points = run_pts;
+        args.n_tiles = run_pts / k.tile_points;
         float2* outp = (float2*)((char*)out + v.out_off);
         args.gin = in;
         args.gout = outp;
@@ -199,7 +222,7 @@ int main(int argc, char** argv)
         std::sort(t.begin(), t.end());
         CK(cudaMemcpy(got.data(), outp, CHK * 8, cudaMemcpyDeviceToHost));
         double rel = 0;
-        auto& rf = ref[k.e][k.mode != MODE_C2C ? 2 + k.mode : (k.reps == 0 ? 2 : k.reorder)];
+        auto& rf = ref[k.e][k.reps > 1 ? 5 + (k.mode != MODE_C2C) : k.mode != MODE_C2C ? 2 + k.mode : (k.reps == 0 ? 2 : k.reorder)];
         if (k.reps == 0 && rf.empty()) {  // staging-only variants must reproduce the input
             rf.resize(CHK);
             CK(cudaMemcpy(rf.data(), in, CHK * 8, cudaMemcpyDeviceToHost));
@@ -216,9 +239,9 @@ int main(int argc, char** argv)
             rel = sqrt(num / den);
         }
         const double med = t[t.size() / 2];
-        printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : (k.mode == MODE_R2C ? "r2c" : k.mode == MODE_C2R ? "c2r" : "fft"), k.e, 1 << k.e, v.b, v.tile_e,
+        printf("%s,%d,%d,%d,%d,%d,%d,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.4f,%.1f,%.3f,%.2e\n", k.reps == 0 ? "stage_copy" : (k.mode == MODE_R2C ? "r2c" : k.mode == MODE_C2R ? "c2r" : "fft"), k.e, 1 << k.e, v.b, v.tile_e,
                k.stages, k.minb, k.io == IO_TMA ? "tma" : (k.io == IO_LDG ? "ldg" : k.io == IO_REG ? "reg" : "tma_stg"), k.tw == TW_LUT ? "lut" : "mufu", k.reorder, k.reps, v.hint,
-               v.out_off, v.promo, v.swz, k.pf, k.skew, k.threads, k.smem_bytes, v.per_sm < 0 ? -1 : per_sm, fa.numRegs, med,
+               v.out_off, v.promo, v.swz, k.pf, k.skew, k.dual, k.threads, k.smem_bytes, v.per_sm < 0 ? -1 : per_sm, fa.numRegs, med,
                t[0], pts * 16.0 / med / 1e6, copy_ms / med, rel);
         fflush(stdout);
     }

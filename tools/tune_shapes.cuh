@@ -177,3 +177,81 @@ static void add_size()
         add_late<E, 5, 11, 2, 4, 0>({4});
     }
 }
+
+// ---- dual-lane shapes (block_fft_dual.cuh): two transforms per thread, threads = 2^(TILE_E - B - 1) ----
+template <int E, int B, int TILE_E, int STAGES, int MINB, int IO, int PF>
+static void add_dual_c2c(std::initializer_list<int> per_sms)
+{
+    if constexpr (TILE_E > E && E - B >= 4 && (TILE_E - B) >= 6 && (TILE_E - B) <= 11) {
+        for (int per : per_sms) {
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 1, IO, TW_LUT, 1, PF, true, 1>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2C, 0, 0, IO, TW_LUT, 1, PF, true, 1>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+        }
+    }
+}
+template <int E, int B, int TILE_E, int STAGES, int MINB, int IO, int PF>
+static void add_dual_real(std::initializer_list<int> per_sms)
+{
+    if constexpr (TILE_E > E && E - B >= 4 && (TILE_E - B) >= 6 && (TILE_E - B) <= 11) {
+        for (int per : per_sms) {
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_R2C, 0, 1, IO, TW_LUT, 1, PF, true, 1>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+            g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, STAGES, MINB, MODE_C2R, 1, 1, IO, TW_LUT, 1, PF, true, 1>(), B, TILE_E});
+            g_variants.back().per_sm = per;
+        }
+    }
+}
+// FFT_multiple (100 in-place repetitions, thread-staged): C2C natural order and R2C
+template <int E, int B, int TILE_E, int MINB, int DUAL>
+static void add_multiple()
+{
+    if constexpr (TILE_E >= E + DUAL && E - B >= (DUAL ? 4 : 1) && (TILE_E - B - DUAL) >= 5 && (TILE_E - B - DUAL) <= 10) {
+        g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, 1, MINB, MODE_C2C, 0, 1, IO_LDG, TW_LUT, 100, 0, true, DUAL>(), B, TILE_E});
+        g_variants.push_back(Variant{make_entry_shape<E, B, TILE_E, 1, MINB, MODE_R2C, 0, 1, IO_LDG, TW_LUT, 100, 0, true, DUAL>(), B, TILE_E});
+    }
+}
+
+// the product shape of each kind next to the dual-lane candidates (same box, same run)
+template <int E>
+static void add_dual_size()
+{
+    add_shape<E, 4, 12, 2, 2>({2});                 // reference outputs for the checks (C2C)
+    add_real<E, 4, 12, 2, 2, IO_TMA, -1>({2});      // (R2C / C2R)
+    // product shapes (tuning.hpp)
+    if constexpr (E == 8) { add_late<E, 4, 10, 2, 8, 1>({6}); add_real<E, 4, 11, 2, 6, IO_TMA, 1>({4}); }
+    if constexpr (E == 9 || E == 10) { add_late<E, 5, 12, 2, 2, 1>({2}); add_real<E, 5, 11, 2, 4, IO_TMA, 1>({4}); add_real<E, 5, 11, 2, 4, IO_TMA_STG, 1>({4}); }
+    if constexpr (E == 11) { add_late<E, 4, 11, 2, 6, 1>({5}); add_real<E, 4, 11, 2, 6, IO_TMA, 1>({6}); }
+    if constexpr (E == 12) { add_late<E, 5, 12, 2, 3, 1>({3}); add_real<E, 4, 12, 2, 3, IO_TMA, 1>({3}); }
+    // dual-lane candidates
+    add_dual_c2c<E, 4, 12, 2, 3, IO_TMA, 1>({2, 3});
+    add_dual_c2c<E, 4, 12, 2, 3, IO_TMA_STG, 1>({2, 3});
+    add_dual_real<E, 4, 12, 2, 3, IO_TMA, 1>({2, 3});
+    add_dual_real<E, 4, 12, 2, 3, IO_TMA_STG, 1>({2, 3});
+    if constexpr (E <= 10) {
+        add_dual_c2c<E, 4, 11, 2, 6, IO_TMA, 1>({4, 6});
+        add_dual_real<E, 4, 11, 2, 6, IO_TMA, 1>({4, 6});
+        add_dual_real<E, 4, 11, 2, 6, IO_TMA_STG, 1>({4, 6});
+    }
+    if constexpr (E >= 9 && E <= 11) {
+        add_dual_c2c<E, 5, 12, 2, 4, IO_TMA, 1>({3, 4});
+        add_dual_real<E, 5, 12, 2, 4, IO_TMA, 1>({3, 4});
+        add_dual_real<E, 5, 12, 2, 4, IO_TMA_STG, 1>({3, 4});
+    }
+    if constexpr (E == 12) {
+        add_dual_c2c<E, 4, 13, 2, 1, IO_TMA, 1>({1});
+        add_dual_c2c<E, 4, 13, 3, 1, IO_TMA, 2>({1});
+        add_dual_real<E, 4, 13, 2, 1, IO_TMA, 1>({1});
+        add_dual_real<E, 4, 13, 3, 1, IO_TMA, 2>({1});
+        add_dual_c2c<E, 5, 13, 3, 1, IO_TMA, 2>({1});
+        add_dual_real<E, 5, 13, 3, 1, IO_TMA, 2>({1});
+    }
+    // FFT_multiple: product shape vs dual
+    using Tm = typename ShapeFor<E, MODE_C2C, 1, 100>::type;
+    add_multiple<E, Tm::B, Tm::TILE_E, Tm::MINB, 0>();
+    add_multiple<E, 4, 12, 3, 1>();
+    add_multiple<E, 4, 11, 6, 1>();
+    add_multiple<E, 5, 12, 4, 1>();
+    add_multiple<E, 4, 13, 1, 1>();
+}

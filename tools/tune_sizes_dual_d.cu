@@ -1,0 +1,3 @@
+// dual-lane shape instances (split so the sweep compiles in parallel)
+#include "tune_shapes.cuh"
+void add_sizes_dual_d() { add_dual_size<11>(); }
