@@ -259,7 +259,7 @@ SMFFT_DEV void fft_pass_compute(float2 (&v)[C::R], int vt, const float2* tw)
     });
 }
 
-template <class C, int PIDX>
+template <class C, int PIDX, class XL = typename C::XLayout>
 SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, int vt)
 {
     constexpr int c = C::radix_log2(PIDX), r = 1 << c, U = C::R / r;
@@ -273,10 +273,10 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
             static_for<r / 2>([&](auto QI) {
                 constexpr int q = 2 * decltype(QI)::value;
                 const float2 lo = v[u + q * U], hi = v[u + (q + 1) * U];
-                plat::sts128(s + C::XLayout::phys(xb + q), make_float4(lo.x, lo.y, hi.x, hi.y));
+                plat::sts128(s + XL::phys(xb + q), make_float4(lo.x, lo.y, hi.x, hi.y));
             });
         } else if constexpr (NS % 256 == 0) {
-            const int p0 = C::XLayout::phys(xb);  // q*NS leaves bits 0..7 alone (SW128 keys on bits 4..6, SW256 on 5..7)
+            const int p0 = XL::phys(xb);  // q*NS leaves bits 0..7 alone (SW128 keys on bits 4..6, SW256 on 5..7)
             static_for<r>([&](auto QI) {
                 constexpr int q = decltype(QI)::value;
                 plat::sts64(s + p0 + q * NS, v[u + q * U]);
@@ -284,7 +284,7 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
         } else {
             static_for<r>([&](auto QI) {
                 constexpr int q = decltype(QI)::value;
-                plat::sts64(s + C::XLayout::phys(xb + q * NS), v[u + q * U]);
+                plat::sts64(s + XL::phys(xb + q * NS), v[u + q * U]);
             });
         }
     });
@@ -308,20 +308,134 @@ SMFFT_DEV HookAt<PASS_, F> hook_at(F f)
     return HookAt<PASS_, F>{f};
 }
 
+// ---- R2C with mirrored ownership in the last pass (RC/FFT-GPU-32bit-Stockham.cu:269-344 without its exchange) ----
+// The real pass needs Z[k] and Z[N-k] together.  When the last pass runs U = 2 butterflies per thread (radix r = R/2,
+// Ns = N/r = 2T virtual threads), the thread may pick WHICH two virtual threads it computes: j = t and the mirror
+// j' = Ns - t (thread 0: j = 0 and j' = T, both their own mirrors).  Its outputs are then k = j + q Ns and
+// N - k = j' + (r-1-q) Ns: every pair (k, N-k) sits in ONE thread and the real pass needs no exchange and no barrier
+// -- 8 STS + 8 LDS + 1 barrier less per 16 points than r2c_tail_regs (the kernels are bound by shared-memory
+// wavefronts, profiles/r01_ncu_summary_z.md).  The last exchange uses a LINEAR layout: its scatter writes and the
+// ascending reads are whole 128-byte rows, and the descending mirror reads j' = Ns - t are conflict-free only there
+// (lane 0 wraps into column 0 of the next row, the one bank pair the other 15 lanes leave free).
+// Twiddles of the mirrored butterfly: W_N^{(Ns - t) q} = W_r^q conj(W_N^{t q});  thread 0: W_N^{T q} = W_{2r}^q.
+template <class C>
+struct MirrorR2C {
+    static constexpr int PL = C::P - 1;
+    static constexpr int r = 1 << C::radix_log2(PL);
+    static constexpr int NS = C::N / r;
+    static constexpr bool OK = !C::DUAL && C::P >= 3 && C::R == 16 && C::R / r == 2 && C::T >= 16 && C::VEC128 && C::REORDER == 1 &&
+                               (1 << C::ns_log2(C::P - 2)) >= 16 && std::is_same<typename C::Layout, LayoutSW128>::value;
+    // index (within the transform) of register m: even m = butterfly j = t, odd m = the mirror butterfly
+    static SMFFT_DEV int index(int t, int m) { return ((m & 1) ? (t == 0 ? C::T : NS - t) : t) + (m >> 1) * NS; }
+};
+
+template <class C>
+SMFFT_DEV void load_mirror(float2 (&v)[C::R], const float2* s, int fbase, int t)
+{
+    using M = MirrorR2C<C>;
+    const float2* a = s + fbase + t;
+    const float2* b = s + fbase + (t == 0 ? C::T : M::NS - t);
+    static_for<C::R / 2>([&](auto Q) {
+        constexpr int q = decltype(Q)::value;
+        v[2 * q] = plat::lds64(a + q * M::NS);
+        v[2 * q + 1] = plat::lds64(b + q * M::NS);
+    });
+}
+
+template <class C>
+SMFFT_DEV void fft_pass_compute_mirror(float2 (&v)[C::R], int t, const float2* tw)
+{
+    using M = MirrorR2C<C>;
+    constexpr int r = M::r;
+    float2 pw[r];
+    make_twiddle_powers<C::DIR, C::TW, C::N, r>(pw, t, tw + C::tw_offset(M::PL));
+    static_for<r>([&](auto QI) {
+        constexpr int q = decltype(QI)::value;
+        if constexpr (q >= 1) {
+            v[2 * q] = cmul(v[2 * q], pw[q]);
+            constexpr float cx = cos64(q * (64 / (2 * r))), sy = C::DIR ? sin64(q * (64 / (2 * r))) : -sin64(q * (64 / (2 * r)));
+            // conj of W_N^{t' q}, t' = t, or T for thread 0 (whose mirror butterfly is j' = T): W_N^{T q} = W_{2r}^q
+            const float2 wc = t == 0 ? make_float2(cx, -sy) : make_float2(pw[q].x, -pw[q].y);
+            v[2 * q + 1] = mul_wconst<C::DIR, q, r>(cmul(v[2 * q + 1], wc));
+        }
+    });
+    dft_regs<C::PACK, C::DIR, r, 0, 2, C::R>(v);
+    dft_regs<C::PACK, C::DIR, r, 1, 2, C::R>(v);
+}
+
+// one pair of the real pass: A = Z[k], Bv = Z[N-k], Wh = W_{2N}^k / 2  ->  lo = X[k], hi = X[N-k] (see r2c_tail_regs)
+SMFFT_DEV void r2c_pair(float2 A, float2 Bv, float2 Wh, float2& lo, float2& hi)
+{
+    const float sx = A.x + Bv.x, sy = A.y - Bv.y, dx = A.x - Bv.x, dy = A.y + Bv.y;
+    const float px = Wh.x * dy + Wh.y * dx, py = Wh.y * dy - Wh.x * dx;
+    lo = make_float2(0.5f * sx + px, 0.5f * sy + py);
+    hi = make_float2(0.5f * sx - px, py - 0.5f * sy);
+}
+
+// real pass on the mirrored ownership, registers only.  On return register m holds X[MirrorR2C::index(t, m)].
+template <class C>
+SMFFT_DEV void r2c_tail_mirror(float2 (&v)[C::R], const float2* tw)
+{
+    using M = MirrorR2C<C>;
+    constexpr int r = M::r;
+    static_assert(4 * r <= 64, "constant twiddles of the mirrored real pass come from the W_64 table");
+    const int t = plat::tid() & (C::T - 1);
+    if (t != 0) {
+        float2 wt;  // W_{2N}^t / 2
+        if constexpr (C::TW == TW_LUT) {
+            wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
+        } else {
+            wt = tw_mufu<0, 2 * C::N>(t);
+            wt.x *= 0.5f;
+            wt.y *= 0.5f;
+        }
+        static_for<r>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;  // k = t + q Ns, N - k = (Ns - t) + (r-1-q) Ns
+            r2c_pair(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<0, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
+        });
+    } else {
+        // j = 0: k = q Ns pairs with (r-q) Ns; bin 0 packs (X[0], X[N]), k = N/2 is its own partner
+        const float2 z0 = v[0], zm = v[r];
+        v[0] = make_float2(z0.x + z0.y, z0.x - z0.y);
+        v[r] = make_float2(zm.x, -zm.y);
+        static_for<r / 2>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;
+            if constexpr (q >= 1)
+                r2c_pair(v[2 * q], v[2 * (r - q)], mul_wconst<0, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
+        });
+        // j' = T: k = T + q Ns pairs with T + (r-1-q) Ns; W_{2N}^k = W_{4r}^{1 + 2q}
+        static_for<r / 2>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;
+            r2c_pair(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<0, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
+                     v[2 * (r - 1 - q) + 1]);
+        });
+    }
+}
+
 // hook() runs once per tile, right after the first barrier following pass Hook::PASS: from the first
 // barrier of a tile onwards every thread of the CTA has finished ALL work of the previous tile, so the
 // previous tile's buffer may be refilled; a later pass shortens the time the refill is in flight.
-template <class C, int PIDX, class Hook>
+template <class C, int PIDX, int XF = 0, class Hook = NoHook>
 SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t, const float2* tw, Hook&& hook)
 {
-    fft_pass_compute<C, PIDX>(v, vt, tw);
+    constexpr bool MIRROR = XF == 1 /* XF_R2C */ && MirrorR2C<C>::OK;
+    if constexpr (MIRROR && PIDX == C::P - 1)
+        fft_pass_compute_mirror<C>(v, t, tw);
+    else
+        fft_pass_compute<C, PIDX>(v, vt, tw);
     if constexpr (PIDX + 1 < C::P) {
         plat::sync_block();  // every thread has finished reading the previous state of the tile
         if constexpr (PIDX == (std::remove_reference<Hook>::type::PASS < C::P - 2 ? std::remove_reference<Hook>::type::PASS : C::P - 2)) hook();
-        fft_pass_scatter<C, PIDX>(v, s, fbase, vt);
-        plat::sync_block();
-        load_natural<C, typename C::XLayout>(v, s, fbase, t);
-        run_passes<C, PIDX + 1>(v, s, fbase, t, t, tw, hook);
+        if constexpr (MIRROR && PIDX + 1 == C::P - 1) {
+            fft_pass_scatter<C, PIDX, LayoutLinear>(v, s, fbase, vt);
+            plat::sync_block();
+            load_mirror<C>(v, s, fbase, t);
+        } else {
+            fft_pass_scatter<C, PIDX>(v, s, fbase, vt);
+            plat::sync_block();
+            load_natural<C, typename C::XLayout>(v, s, fbase, t);
+        }
+        run_passes<C, PIDX + 1, XF>(v, s, fbase, t, t, tw, hook);
     }
 }
 
@@ -410,7 +524,7 @@ SMFFT_DEV void block_fft_regs(float2 (&v)[C::R], float2* s, const float2* tw, Ho
         vt = noreorder_vid<C>(t);
         load_rows_brev<C>(v, s, fbase, vt);
     }
-    run_passes<C, 0>(v, s, fbase, vt, t, tw, hook);
+    run_passes<C, 0, XF>(v, s, fbase, vt, t, tw, hook);
 }
 
 // R2C tail, pair form.  On entry v[m] = Z[t + m*T].  Thread t evaluates the R/2 pairs (k, N-k), k = t + i*T < N/2:
@@ -430,13 +544,20 @@ SMFFT_DEV int r2c_hi_index(int t, int i)
 template <class C>
 SMFFT_DEV int r2c_out_index(int t, int m)
 {
-    return m < C::R / 2 ? t + m * C::T : r2c_hi_index<C>(t, m - C::R / 2);
+    if constexpr (MirrorR2C<C>::OK)
+        return MirrorR2C<C>::index(t, m);
+    else
+        return m < C::R / 2 ? t + m * C::T : r2c_hi_index<C>(t, m - C::R / 2);
 }
 
 template <class C>
 SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
 {
     static_assert(2 * C::R <= 64, "constant twiddles W_{2R}^i come from the W_64 table");
+    if constexpr (MirrorR2C<C>::OK) {  // every pair already sits in one thread (run_passes<.., XF_R2C>): no exchange
+        r2c_tail_mirror<C>(v, tw);
+        return;
+    }
     constexpr int H = C::R / 2;
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
@@ -592,7 +713,7 @@ SMFFT_DEV void block_fft_preloaded_to_global(float2 (&v)[C::R], float2* s, const
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
-    run_passes<C, 0>(v, s, fbase, t, t, tw, NoHook{});
+    run_passes<C, 0, XF>(v, s, fbase, t, t, tw, NoHook{});
     if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
     store_global_result<C, XF>(v, g, valid);
 }
