@@ -39,7 +39,8 @@ namespace detail {
 //            reference-compatible device API);  XLayout_: layout used by the exchanges between passes.
 // VEC128_  : allow 16-byte shared accesses (needs a 16-byte aligned tile).
 // SKEW_    : de-conflict the natural accesses of small transforms (T < 16) with skewed rows + selects.
-// DUAL_    : 2 = packed f32x2 add / subtract on (re, im) in the butterflies (same threads, fewer issue slots);
+// DUAL_    : bit flags.  2 = packed f32x2 add / subtract on (re, im) in the butterflies (same threads, fewer issue slots);
+//            4 = reversed pass plan (small radix first; lets the C2R pass own its pairs, see MirrorC2R);
 //            1 = one thread carries the same points of TWO transforms of the tile in the packed f32x2 lanes
 //            (block_fft_dual.cuh): half the threads, half the floating-point and exchange instructions per point.
 template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128, class XLayout_ = Layout_,
@@ -53,10 +54,12 @@ struct BlockCfg {
     static constexpr int T = 1 << A;    // threads per FFT
     static constexpr int F = F_;        // FFTs per tile (power of two)
     static constexpr int L = F_ * N;    // points per tile
-    static constexpr int DUAL = DUAL_ == 1;
-    static constexpr int PACK = DUAL_ == 2;  // one transform per thread, packed (re, im) add / subtract in the butterflies
+    static constexpr int DUAL = DUAL_ & 1;
+    static constexpr int PACK = (DUAL_ >> 1) & 1;  // one transform per thread, packed (re, im) add / subtract in the butterflies
+    static constexpr int REV = (DUAL_ >> 2) & 1;   // pass plan with the small radix FIRST: [2^(E mod B), R, .., R]
     static constexpr int THREADS = (F_ * T) >> DUAL;
-    static_assert(DUAL_ == 0 || DUAL_ == 2 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
+    static_assert(DUAL_ >= 0 && DUAL_ < 8 && (!REV || (E_ % B_ == 3 && VEC128_)), "reversed plans: first radix 8 only");
+    static_assert((DUAL_ & 1) == 0 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
                                  std::is_same<Layout_, LayoutSW128>::value && VEC128_),
                   "dual-lane transforms: an even number of transforms per tile, T >= 16, N >= 128, R >= 16, SW128 tile");
     static constexpr int DIR = DIR_;          // 0 forward (exp -), 1 inverse (exp +): FFT_Params::fft_direction
@@ -69,9 +72,9 @@ struct BlockCfg {
     static constexpr bool SAME_LAYOUT = std::is_same<Layout_, XLayout_>::value;
     static_assert(E_ > B_, "need at least two threads per FFT");
     static_assert(B_ >= 1 && B_ <= 5, "1..32 points per thread");
-    // pass plan, large radix first: [R, R, .., R, 2^(E mod B)]
+    // pass plan, large radix first: [R, R, .., R, 2^(E mod B)]  (REV: [2^(E mod B), R, .., R])
     static constexpr int P = (E + B - 1) / B;
-    static SMFFT_CX int radix_log2(int p) { return p < E / B ? B : E % B; }
+    static SMFFT_CX int radix_log2(int p) { return (REV && E % B != 0) ? (p == 0 ? E % B : B) : (p < E / B ? B : E % B); }
     static SMFFT_CX int ns_log2(int p)
     {
         int s = 0;
@@ -144,7 +147,7 @@ template <class C, class LY = typename C::Layout>
 SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t)
 {
     using NA = NaturalAccess<C, LY>;
-    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value) {
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value && !std::is_same<LY, LayoutSW128H>::value) {
         const int p0 = LY::phys(fbase + t);  // bits 4..6 do not depend on m
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
@@ -173,7 +176,7 @@ template <class C, class LY = typename C::Layout>
 SMFFT_DEV void store_natural(const float2 (&v)[C::R], float2* s, int fbase, int t)
 {
     using NA = NaturalAccess<C, LY>;
-    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value) {
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value && !std::is_same<LY, LayoutSW128H>::value) {
         const int p0 = LY::phys(fbase + t);
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
@@ -260,13 +263,13 @@ SMFFT_DEV void fft_pass_compute(float2 (&v)[C::R], int vt, const float2* tw)
 }
 
 template <class C, int PIDX, class XL = typename C::XLayout>
-SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, int vt)
+SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, int vt, int j1 = -1)
 {
     constexpr int c = C::radix_log2(PIDX), r = 1 << c, U = C::R / r;
     constexpr int LNS = C::ns_log2(PIDX), NS = 1 << LNS;
     static_for<U>([&](auto UI) {
         constexpr int u = decltype(UI)::value;
-        const int j = vt + u * C::T;
+        const int j = (u == 1 && j1 >= 0) ? j1 : vt + u * C::T;  // j1: virtual thread of butterfly 1 (mirrored ownership)
         const int xb = fbase + ((j >> LNS) << (LNS + c)) + (j & (NS - 1));
         if constexpr (NS == 1 && C::VEC128) {
             // r contiguous outputs per butterfly: 128-bit stores
@@ -306,6 +309,85 @@ template <int PASS_, class F>
 SMFFT_DEV HookAt<PASS_, F> hook_at(F f)
 {
     return HookAt<PASS_, F>{f};
+}
+
+// layout of the exchange that follows pass PIDX
+template <class C, int PIDX>
+struct ExchangeLayout {
+    static constexpr bool H = C::ns_log2(PIDX) == 3 && std::is_same<typename C::XLayout, LayoutSW128>::value;
+    using type = typename std::conditional<H, LayoutSW128H, typename C::XLayout>::type;
+};
+// the layout the LAST pass reads from = where the in-place result must not be written without a barrier
+template <class C>
+struct LastExchangeSameAsTile {
+    static constexpr bool value = C::P < 2 || std::is_same<typename ExchangeLayout<C, (C::P >= 2 ? C::P - 2 : 0)>::type, typename C::Layout>::value;
+};
+
+// ---- C2R with mirrored ownership in the FIRST pass (reversed plan) ------------------------------------------------
+// The mirror image of MirrorR2C: with the small radix first (r0 = R/2, U = 2 butterflies per thread) the first pass reads
+// x = j + q 2T for two virtual threads j; choosing j = t and j' = 2T - t (thread 0: 0 and T) puts Y[k] and Y[N-k] in one
+// thread, so the inverse real pass runs in pair form on registers: 16 instead of 32 LDS per thread and 12 instead of 20
+// floating-point instructions per pair.  Pass 0 has no twiddles (Ns = 1); only its scatter uses j' for the second butterfly.
+template <class C>
+struct MirrorC2R {
+    static constexpr int r = 1 << C::radix_log2(0);
+    static constexpr int NS2 = C::N / r;  // = 2T
+    static constexpr bool OK = !C::DUAL && C::REV && C::P >= 2 && C::R == 16 && C::R / r == 2 && C::T >= 16 && C::VEC128 &&
+                               C::REORDER == 1 && std::is_same<typename C::Layout, LayoutSW128>::value;
+    static SMFFT_DEV int mirror_j(int t) { return t == 0 ? C::T : NS2 - t; }
+};
+
+// one pair of the inverse real pass: A = Y[k], Bv = Y[N-k], Wh = exp(+2 pi i k / 2N) / 2  ->  zk = Z[k], zn = Z[N-k]
+// (real_combine<1> evaluated for k and for N-k, sharing the sums: W^{N-k} = -conj W^k)
+SMFFT_DEV void c2r_pair(float2 A, float2 Bv, float2 Wh, float2& zk, float2& zn)
+{
+    const float sx = A.x + Bv.x, sy = A.y + Bv.y, dx = A.x - Bv.x, dy = A.y - Bv.y;
+    const float p = Wh.x * sy + Wh.y * dx, q = Wh.y * sy - Wh.x * dx;
+    zk = make_float2(0.5f * sx - p, 0.5f * dy - q);
+    zn = make_float2(0.5f * sx + p, -0.5f * dy - q);
+}
+
+// v[2q] = Y[t + q 2T], v[2q+1] = Y[j' + q 2T] from the (read-only, SW128) tile, then the inverse real pass on the pairs
+template <class C>
+SMFFT_DEV void c2r_head_mirror(float2 (&v)[C::R], const float2* s, int fbase, int t, const float2* tw)
+{
+    using M = MirrorC2R<C>;
+    constexpr int r = M::r;
+    static_assert(4 * r <= 64, "constant twiddles of the mirrored real pass come from the W_64 table");
+    const int jm = M::mirror_j(t);
+    static_for<r>([&](auto QI) {
+        constexpr int q = decltype(QI)::value;
+        v[2 * q] = plat::lds64(s + C::Layout::phys(fbase + t + q * M::NS2));
+        v[2 * q + 1] = plat::lds64(s + C::Layout::phys(fbase + jm + q * M::NS2));
+    });
+    if (t != 0) {
+        float2 wt;  // exp(+2 pi i t / 2N) / 2
+        if constexpr (C::TW == TW_LUT) {
+            wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
+        } else {
+            wt = tw_mufu<1, 2 * C::N>(t);
+            wt.x *= 0.5f;
+            wt.y *= 0.5f;
+        }
+        static_for<r>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;  // k = t + q 2T, N - k = (2T - t) + (r-1-q) 2T
+            c2r_pair(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<1, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
+        });
+    } else {
+        const float2 y0 = v[0], ym = v[r];
+        v[0] = make_float2(0.5f * (y0.x + y0.y), 0.5f * (y0.x - y0.y));  // bin 0 un-packed (RC:280-286)
+        v[r] = make_float2(ym.x, -ym.y);                                 // k = N/2 is its own partner
+        static_for<r / 2>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;
+            if constexpr (q >= 1)
+                c2r_pair(v[2 * q], v[2 * (r - q)], mul_wconst<1, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
+        });
+        static_for<r / 2>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;  // k = T + q 2T
+            c2r_pair(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<1, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
+                     v[2 * (r - 1 - q) + 1]);
+        });
+    }
 }
 
 // ---- R2C with mirrored ownership in the last pass (RC/FFT-GPU-32bit-Stockham.cu:269-344 without its exchange) ----
@@ -426,14 +508,18 @@ SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t
     if constexpr (PIDX + 1 < C::P) {
         plat::sync_block();  // every thread has finished reading the previous state of the tile
         if constexpr (PIDX == (std::remove_reference<Hook>::type::PASS < C::P - 2 ? std::remove_reference<Hook>::type::PASS : C::P - 2)) hook();
+        using XL = typename ExchangeLayout<C, PIDX>::type;
         if constexpr (MIRROR && PIDX + 1 == C::P - 1) {
             fft_pass_scatter<C, PIDX, LayoutLinear>(v, s, fbase, vt);
             plat::sync_block();
             load_mirror<C>(v, s, fbase, t);
         } else {
-            fft_pass_scatter<C, PIDX>(v, s, fbase, vt);
+            if constexpr (XF == 2 /* XF_C2R */ && MirrorC2R<C>::OK && PIDX == 0)
+                fft_pass_scatter<C, PIDX, XL>(v, s, fbase, vt, MirrorC2R<C>::mirror_j(t));
+            else
+                fft_pass_scatter<C, PIDX, XL>(v, s, fbase, vt);
             plat::sync_block();
-            load_natural<C, typename C::XLayout>(v, s, fbase, t);
+            load_natural<C, XL>(v, s, fbase, t);
         }
         run_passes<C, PIDX + 1, XF>(v, s, fbase, t, t, tw, hook);
     }
@@ -517,7 +603,9 @@ SMFFT_DEV void block_fft_regs(float2 (&v)[C::R], float2* s, const float2* tw, Ho
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
     int vt = t;
-    if constexpr (C::REORDER) {
+    if constexpr (XF == XF_C2R && MirrorC2R<C>::OK) {
+        c2r_head_mirror<C>(v, s, fbase, t, tw);  // tile is read-only here: no barrier
+    } else if constexpr (C::REORDER) {
         load_natural<C>(v, s, fbase, t);
         if constexpr (XF == XF_C2R) real_pass_regs<C, 1>(v, s, fbase, t, tw);  // tile is read-only here: no barrier
     } else {
@@ -563,7 +651,7 @@ SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
     // same layout: these are slots this thread read in the last pass, no barrier needed before
-    if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+    if constexpr ((!C::SAME_LAYOUT || !LastExchangeSameAsTile<C>::value) && C::P > 1) plat::sync_block();
     static_for<H>([&](auto II) {
         constexpr int m = H + decltype(II)::value;
         plat::sts64(s + C::Layout::phys(fbase + t + m * C::T), v[m]);
@@ -635,7 +723,7 @@ SMFFT_DEV void block_fft_tile(float2* s, const float2* tw, Hook&& hook = Hook{})
             plat::sync_block();  // every partner has been read before the packed spectrum overwrites Z
         } else {
             // with distinct entry/exchange layouts the final slots are not the ones this thread just read
-            if constexpr (!C::SAME_LAYOUT && C::P > 1) plat::sync_block();
+            if constexpr ((!C::SAME_LAYOUT || !LastExchangeSameAsTile<C>::value) && C::P > 1) plat::sync_block();
         }
         store_result<C, XF>(v, s, (tid >> C::A) << C::E, tid & (C::T - 1));
     }

@@ -27,6 +27,13 @@ struct LayoutSW256 {
     static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 5) & 7) << 1); }
 };
 
+// exchange layout for a scatter with Ns = 8 (reversed plans, small radix first): sixteen consecutive virtual threads write
+// the same eight columns of two rows that are eight rows apart (same SW128 key); bit 3 of the row flips the upper chunk
+// bit so the two groups land on different halves of the banks
+struct LayoutSW128H {
+    static SMFFT_HOST_DEV int phys(int x) { return x ^ ((((x >> 4) & 7) ^ (((x >> 7) & 1) << 2)) << 1); }
+};
+
 struct LayoutLinear {
     static SMFFT_HOST_DEV int phys(int x) { return x; }
 };

@@ -132,8 +132,8 @@ struct TuningReal<12> {
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
 
-// arithmetic flavour of one kernel instance (BlockCfg::DUAL_): 0 = scalar, 1 = dual-lane, 2 = packed (re, im) add / subtract
-// in the butterflies.  Packed add / subtract removes ~9 % of the issue slots; it pays where a kernel is issue-bound
+// arithmetic flavour of one kernel instance (BlockCfg::DUAL_, bit flags): 0 = scalar, 1 = dual-lane, 2 = packed (re, im)
+// add / subtract in the butterflies, 4 = reversed pass plan.  Packed add / subtract removes ~9 % of the issue slots; it pays where a kernel is issue-bound
 // (interleaved A/B against the all-scalar build, profiles/r01_ab_scalar_vs_product.json and ..._vs_packed_all.json:
 // C2R -1.4..-7.7 % at every size, R2C of 4096 / 8192 reals -4..-6 %, FFT_multiple -2..-11 %) and is neutral or slightly
 // negative (+-1 %) for the HBM-bound C2C external kernels and the other R2C sizes, which stay scalar; the R = 32 R2C
@@ -149,6 +149,7 @@ struct ArithFor {
     static constexpr int value = SMFFT_FORCE_ARITH;
 #else
     static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : 2)
+                                 : (MODE == 2 && E == 11) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
                                  : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2 : 0;
 #endif
 };

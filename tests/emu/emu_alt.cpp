@@ -1,0 +1,79 @@
+// emu_alt.cpp -- non-product shapes on the SIMT emulator: reference-contract configuration, other radix plans, late
+// prefetch, register-direct input, reversed plans (own translation unit: compiles in parallel).  TESTS ONLY.
+#include "emu_run_cfg.hpp"
+
+extern "C" {
+
+int emu_run_compat(const void* in, void* out, int e, long long n_ffts, int mode, int dir, int reorder, double* bank_factor)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+#define CC(E)                                                                                      \
+    if (e == E) {                                                                                  \
+        if (mode == 0 && dir == 0 && reorder == 1) return run_compat<E, 0, 0, 1>(i, o, n_ffts, bank_factor); \
+        if (mode == 0 && dir == 0 && reorder == 0) return run_compat<E, 0, 0, 0>(i, o, n_ffts, bank_factor); \
+        if (mode == 0 && dir == 1 && reorder == 1) return run_compat<E, 0, 1, 1>(i, o, n_ffts, bank_factor); \
+        if (mode == 0 && dir == 1 && reorder == 0) return run_compat<E, 0, 1, 0>(i, o, n_ffts, bank_factor); \
+        if (mode == 1) return run_compat<E, 1, 0, 1>(i, o, n_ffts, bank_factor);                     \
+        if (mode == 2) return run_compat<E, 2, 1, 1>(i, o, n_ffts, bank_factor);                     \
+    }
+    CC(5) CC(6) CC(7) CC(8) CC(9) CC(10) CC(11) CC(12)
+#undef CC
+    return -1;
+}
+
+// alternative shapes: exercise the generic pass machinery (other radices, tile sizes, stage counts)
+int emu_run_alt(const void* in, void* out, int variant, long long n_ffts, int dir, int reorder, int io, int tw, int grid,
+                double* bank_factor)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+    switch (variant) {
+        case 0: return run_shape<10, 3, 1, 0, 1, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 1024 = 8*8*8*2, R=8
+        case 1: return run_shape<10, 5, 4, 0, 3, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 1024 = 32*32, 3 stages
+        case 2: return run_shape<9, 3, 4, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);    // 512 = 8*8*8
+        case 3: return run_shape<7, 2, 8, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);    // 128, R=4 (compat shape)
+        case 4: return run_shape<12, 4, 2, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 2 x 4096 per tile
+        case 5: return run_shape<6, 3, 16, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 64 = 8*8
+        case 6: return run_shape<5, 2, 16, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 32 = 4*4*2
+        case 7: return run_shape<11, 5, 1, 0, 2, 1>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor);   // 2048 = 32*32*2
+    }
+    return -1;
+}
+
+// late prefetch (the refill of the previous buffer issued after pass PF instead of at the first barrier)
+int emu_run_late(const void* in, void* out, int variant, long long n_ffts, int grid)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+    switch (variant) {
+        case 0: return run_cfg<12, 4, 1, 0, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);
+        case 1: return run_cfg<12, 4, 1, 0, 1, 0, kernels::IO_TMA_STG, TW_LUT, 2, 1, 2>(i, o, n_ffts, grid, nullptr);
+        case 2: return run_cfg<10, 4, 4, 0, 0, 0, kernels::IO_TMA, TW_LUT, 2, 1, 2>(i, o, n_ffts, grid, nullptr);
+        case 3: return run_cfg<8, 4, 8, 0, 0, 1, kernels::IO_TMA_STG, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);   // P = 2: clamps to pass 0
+        case 4: return run_cfg<10, 4, 4, 1, 0, 1, kernels::IO_TMA_STG, TW_LUT, 3, 1, 1>(i, o, n_ffts, grid, nullptr);  // R2C, three buffers
+        case 5: return run_cfg<11, 4, 2, 2, 1, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);      // C2R
+        // register-direct input (IO_REG): global -> registers, with and without the software prefetch
+        case 6: return run_cfg<10, 4, 1, 0, 0, 1, kernels::IO_REG, TW_LUT, 1, 1, 0>(i, o, n_ffts, grid, nullptr);
+        case 7: return run_cfg<9, 5, 4, 0, 1, 1, kernels::IO_REG, TW_LUT, 1, 1, -1>(i, o, n_ffts, grid, nullptr);
+        case 8: return run_cfg<10, 4, 2, 1, 0, 1, kernels::IO_REG, TW_LUT, 1, 1, 0>(i, o, n_ffts, grid, nullptr);     // R2C
+        case 9: return run_cfg<7, 4, 8, 1, 0, 1, kernels::IO_REG, TW_LUT, 1, 1, -1>(i, o, n_ffts, grid, nullptr);     // R2C
+        // reversed plan [8,16,16] with the mirrored C2R head (arith flags 6 = packed add/sub + reversed), TMA / LDG / TMA_STG / MUFU
+        case 10: return run_cfg<11, 4, 1, 2, 1, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 6>(i, o, n_ffts, grid, nullptr);
+        case 11: return run_cfg<11, 4, 2, 2, 1, 1, kernels::IO_LDG, TW_LUT, 1, 1, 0, 4>(i, o, n_ffts, grid, nullptr);
+        case 12: return run_cfg<11, 4, 1, 2, 1, 1, kernels::IO_TMA_STG, TW_MUFU, 2, 1, 1, 6>(i, o, n_ffts, grid, nullptr);
+        // reversed plan, plain C2C (both directions) and R2C through the same machinery
+        case 13: return run_cfg<11, 4, 1, 0, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 4>(i, o, n_ffts, grid, nullptr);
+        case 14: return run_cfg<11, 4, 1, 0, 1, 1, kernels::IO_LDG, TW_LUT, 1, 1, 0, 4>(i, o, n_ffts, grid, nullptr);
+        case 15: return run_cfg<7, 4, 8, 0, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, -1, 4>(i, o, n_ffts, grid, nullptr);   // [8,16]
+    }
+    return -1;
+}
+
+int emu_alt_length(int variant)
+{
+    static const int n[] = {1024, 1024, 512, 128, 4096, 64, 32, 2048};
+    return variant >= 0 && variant < 8 ? n[variant] : -1;
+}
+
+}
