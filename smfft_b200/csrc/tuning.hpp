@@ -137,12 +137,19 @@ struct TuningReal<12> {
 // (interleaved A/B against the all-scalar build, profiles/r01_ab_scalar_vs_product.json and ..._vs_packed_all.json:
 // C2R -1.4..-7.7 % at every size, R2C of 4096 / 8192 reals -4..-6 %, FFT_multiple -2..-11 %) and is neutral or slightly
 // negative (+-1 %) for the HBM-bound C2C external kernels and the other R2C sizes, which stay scalar; the R = 32 R2C
-// FFT_multiple shapes (512 / 1024 points) lose 1-3 % and stay scalar too.
+// FFT_multiple shapes (512 / 1024 points) lose 1-3 % and stay scalar too.  Under the sustained load of the 16-launch
+// bench step (power-capped clocks) the three-pass R = 16 C2C kernels gain as well -- 2048 points -3..-5 %, 4096 points
+// no-reorder -4 % (profiles/r01_bench_sustained_scalar_vs_packed.json) -- the R = 32 shapes do not (+1 %).
 // The dual-lane form (block_fft_dual.cuh: two transforms per thread, ALL arithmetic and exchanges packed, half the
 // instructions per point) is NOT used by the product: it also halves the resident warps, and the large and real
 // kernels turn out to be bound by shared-memory wavefronts and latency, not by issue slots alone
 // (profiles/r01_tune_dual_a.csv: equal at 2048 points, 3-12 % slower elsewhere).  It stays as a measured experiment
 // with emulator coverage (tools/tune_dual, tests/test_emu_kernels.py).
+#if defined(SMFFT_R32_E12)
+constexpr bool kNoR32E12 = false;
+#else
+constexpr bool kNoR32E12 = true;
+#endif
 template <int E, int MODE, int REORDER, int REPS>
 struct ArithFor {
 #if defined(SMFFT_FORCE_ARITH)
@@ -150,7 +157,8 @@ struct ArithFor {
 #else
     static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : 2)
                                  : (MODE == 2 && E == 11) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
-                                 : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2 : 0;
+                                 : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2
+                                 : (MODE == 0 && (E == 11 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans, sustained load
 #endif
 };
 
@@ -159,7 +167,14 @@ struct ArithFor {
 // 1.28 / 1.27 ms, not at 4096)
 template <int E, int MODE, int REORDER, int REPS>
 struct ShapeFor {
+    // 4096 points: the R = 32 plan [32,32,4] wins single launches (1.335 vs 1.36 ms) but runs 12 warps per SM and loses
+    // under the sustained, power-capped load of the bench step (1.47 vs 1.42 ms for R = 16 with packed add / subtract,
+    // profiles/r01_bench_sustained_r32_vs_r16_4096.json); SMFFT_R32_E12 brings it back for experiments
+#if defined(SMFFT_R32_E12)
     static constexpr bool R32 = REORDER == 1 && ((MODE == 0 && (E == 9 || E == 10 || (E == 12 && REPS == 1))) ||
+#else
+    static constexpr bool R32 = REORDER == 1 && ((MODE == 0 && (E == 9 || E == 10)) ||
+#endif
                                                  (MODE != 0 && REPS > 1 && (E == 9 || E == 10)));
     static constexpr bool REAL = MODE != 0 && REPS == 1;
     using type = typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type;
