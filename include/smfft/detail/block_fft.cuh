@@ -339,9 +339,11 @@ struct MirrorC2R {
 
 // one pair of the inverse real pass: A = Y[k], Bv = Y[N-k], Wh = exp(+2 pi i k / 2N) / 2  ->  zk = Z[k], zn = Z[N-k]
 // (real_combine<1> evaluated for k and for N-k, sharing the sums: W^{N-k} = -conj W^k)
+template <int PACK>
 SMFFT_DEV void c2r_pair(float2 A, float2 Bv, float2 Wh, float2& zk, float2& zn)
 {
-    const float sx = A.x + Bv.x, sy = A.y + Bv.y, dx = A.x - Bv.x, dy = A.y - Bv.y;
+    const float2 sm = cadd_p<PACK>(A, Bv), df = csub_p<PACK>(A, Bv);
+    const float sx = sm.x, sy = sm.y, dx = df.x, dy = df.y;
     const float p = Wh.x * sy + Wh.y * dx, q = Wh.y * sy - Wh.x * dx;
     zk = make_float2(0.5f * sx - p, 0.5f * dy - q);
     zn = make_float2(0.5f * sx + p, -0.5f * dy - q);
@@ -371,7 +373,7 @@ SMFFT_DEV void c2r_head_mirror(float2 (&v)[C::R], const float2* s, int fbase, in
         }
         static_for<r>([&](auto QI) {
             constexpr int q = decltype(QI)::value;  // k = t + q 2T, N - k = (2T - t) + (r-1-q) 2T
-            c2r_pair(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<1, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
+            c2r_pair<C::PACK>(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<1, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
         });
     } else {
         const float2 y0 = v[0], ym = v[r];
@@ -380,11 +382,11 @@ SMFFT_DEV void c2r_head_mirror(float2 (&v)[C::R], const float2* s, int fbase, in
         static_for<r / 2>([&](auto QI) {
             constexpr int q = decltype(QI)::value;
             if constexpr (q >= 1)
-                c2r_pair(v[2 * q], v[2 * (r - q)], mul_wconst<1, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
+                c2r_pair<C::PACK>(v[2 * q], v[2 * (r - q)], mul_wconst<1, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
         });
         static_for<r / 2>([&](auto QI) {
             constexpr int q = decltype(QI)::value;  // k = T + q 2T
-            c2r_pair(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<1, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
+            c2r_pair<C::PACK>(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<1, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
                      v[2 * (r - 1 - q) + 1]);
         });
     }
@@ -446,9 +448,11 @@ SMFFT_DEV void fft_pass_compute_mirror(float2 (&v)[C::R], int t, const float2* t
 }
 
 // one pair of the real pass: A = Z[k], Bv = Z[N-k], Wh = W_{2N}^k / 2  ->  lo = X[k], hi = X[N-k] (see r2c_tail_regs)
+template <int PACK>
 SMFFT_DEV void r2c_pair(float2 A, float2 Bv, float2 Wh, float2& lo, float2& hi)
 {
-    const float sx = A.x + Bv.x, sy = A.y - Bv.y, dx = A.x - Bv.x, dy = A.y + Bv.y;
+    const float2 sm = cadd_p<PACK>(A, Bv), df = csub_p<PACK>(A, Bv);  // (sx, dy), (dx, sy)
+    const float sx = sm.x, sy = df.y, dx = df.x, dy = sm.y;
     const float px = Wh.x * dy + Wh.y * dx, py = Wh.y * dy - Wh.x * dx;
     lo = make_float2(0.5f * sx + px, 0.5f * sy + py);
     hi = make_float2(0.5f * sx - px, py - 0.5f * sy);
@@ -473,7 +477,7 @@ SMFFT_DEV void r2c_tail_mirror(float2 (&v)[C::R], const float2* tw)
         }
         static_for<r>([&](auto QI) {
             constexpr int q = decltype(QI)::value;  // k = t + q Ns, N - k = (Ns - t) + (r-1-q) Ns
-            r2c_pair(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<0, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
+            r2c_pair<C::PACK>(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<0, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
         });
     } else {
         // j = 0: k = q Ns pairs with (r-q) Ns; bin 0 packs (X[0], X[N]), k = N/2 is its own partner
@@ -483,12 +487,12 @@ SMFFT_DEV void r2c_tail_mirror(float2 (&v)[C::R], const float2* tw)
         static_for<r / 2>([&](auto QI) {
             constexpr int q = decltype(QI)::value;
             if constexpr (q >= 1)
-                r2c_pair(v[2 * q], v[2 * (r - q)], mul_wconst<0, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
+                r2c_pair<C::PACK>(v[2 * q], v[2 * (r - q)], mul_wconst<0, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
         });
         // j' = T: k = T + q Ns pairs with T + (r-1-q) Ns; W_{2N}^k = W_{4r}^{1 + 2q}
         static_for<r / 2>([&](auto QI) {
             constexpr int q = decltype(QI)::value;
-            r2c_pair(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<0, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
+            r2c_pair<C::PACK>(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<0, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
                      v[2 * (r - 1 - q) + 1]);
         });
     }
@@ -540,10 +544,11 @@ enum { XF_C2C = 0, XF_R2C = 1, XF_C2R = 2 };  // what one tile computes (kernels
 //   forward: X = ( s.x/2 + Wh.x s.y + Wh.y d.x ,  d.y/2 - Wh.x d.x + Wh.y s.y )
 //   inverse: Z = ( s.x/2 - Wh.x s.y - Wh.y d.x ,  d.y/2 + Wh.x d.x - Wh.y s.y )   (Wh already conjugated)
 // -- the reference's H1 + W H2 (RC:292-307) with the constants folded in: 4 adds + 6 FMAs.
-template <int INVERSE>
+template <int INVERSE, int PACK = 0>
 SMFFT_DEV float2 real_combine(float2 A, float2 B, float2 Wh)
 {
-    const float sx = A.x + B.x, sy = A.y + B.y, dx = A.x - B.x, dy = A.y - B.y;
+    const float2 sm = cadd_p<PACK>(A, B), df = csub_p<PACK>(A, B);
+    const float sx = sm.x, sy = sm.y, dx = df.x, dy = df.y;
     float2 o;
     if constexpr (!INVERSE) {
         o.x = 0.5f * sx + (Wh.x * sy + Wh.y * dx);
@@ -582,7 +587,7 @@ SMFFT_DEV void real_pass_regs(float2 (&v)[C::R], const float2* s, int fbase, int
         if constexpr (m == 0) {
             // t == 0 owns bin 0, which has no partner: (X[0], X[N]) packed / un-packed (RC:280-286, 332-340)
             const float2 Bv = plat::lds64(s + C::Layout::phys(t == 0 ? fbase : xp));
-            float2 out = real_combine<INVERSE>(v[0], Bv, wm[0]);
+            float2 out = real_combine<INVERSE, C::PACK>(v[0], Bv, wm[0]);
             if (t == 0) {
                 const float sc = INVERSE ? 0.5f : 1.0f;
                 out = make_float2(sc * (v[0].x + v[0].y), sc * (v[0].x - v[0].y));
@@ -590,7 +595,7 @@ SMFFT_DEV void real_pass_regs(float2 (&v)[C::R], const float2* s, int fbase, int
             v[0] = out;
         } else {
             const float2 Bv = plat::lds64(s + C::Layout::phys(xp - m * C::T));
-            v[m] = real_combine<INVERSE>(v[m], Bv, wm[m]);
+            v[m] = real_combine<INVERSE, C::PACK>(v[m], Bv, wm[m]);
         }
     });
 }
@@ -672,10 +677,8 @@ SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
         const float2 A = v[i];
         const int xb = (i == 0 && t == 0) ? fbase + C::N / 2 : fbase + C::N - t - i * C::T;
         const float2 Bv = plat::lds64(s + C::Layout::phys(xb));
-        const float sx = A.x + Bv.x, sy = A.y - Bv.y, dx = A.x - Bv.x, dy = A.y + Bv.y;
-        const float px = Wh.x * dy + Wh.y * dx, py = Wh.y * dy - Wh.x * dx;
-        float2 lo = make_float2(0.5f * sx + px, 0.5f * sy + py);
-        float2 hi = make_float2(0.5f * sx - px, py - 0.5f * sy);
+        float2 lo, hi;
+        r2c_pair<C::PACK>(A, Bv, Wh, lo, hi);
         if constexpr (i == 0) {
             if (t == 0) {
                 lo = make_float2(A.x + A.y, A.x - A.y);

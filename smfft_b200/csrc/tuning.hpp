@@ -169,7 +169,8 @@ template <int E, int MODE, int REORDER, int REPS>
 struct ShapeFor {
     // 4096 points: the R = 32 plan [32,32,4] wins single launches (1.335 vs 1.36 ms) but runs 12 warps per SM and loses
     // under the sustained, power-capped load of the bench step (1.47 vs 1.42 ms for R = 16 with packed add / subtract,
-    // profiles/r01_bench_sustained_r32_vs_r16_4096.json); SMFFT_R32_E12 brings it back for experiments
+    // profiles/r01_bench_sustained_r32_vs_r16_4096.json); SMFFT_R32_E12 brings it back for experiments.  The same test for
+    // 512 / 1024 points keeps R = 32 (profiles/r01_bench_sustained_r16_512_1024.json: 6462 vs 6435 GB/s for the step)
 #if defined(SMFFT_R32_E12)
     static constexpr bool R32 = REORDER == 1 && ((MODE == 0 && (E == 9 || E == 10 || (E == 12 && REPS == 1))) ||
 #else
