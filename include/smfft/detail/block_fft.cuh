@@ -315,7 +315,8 @@ SMFFT_DEV HookAt<PASS_, F> hook_at(F f)
 template <class C, int PIDX>
 struct ExchangeLayout {
     static constexpr bool H = C::ns_log2(PIDX) == 3 && std::is_same<typename C::XLayout, LayoutSW128>::value;
-    using type = typename std::conditional<H, LayoutSW128H, typename C::XLayout>::type;
+    static constexpr bool Q = C::REV && PIDX == 0 && C::radix_log2(0) == 3 && std::is_same<typename C::XLayout, LayoutSW128>::value;
+    using type = typename std::conditional<H, LayoutSW128H, typename std::conditional<Q, LayoutSW128Q, typename C::XLayout>::type>::type;
 };
 // the layout the LAST pass reads from = where the in-place result must not be written without a barrier
 template <class C>
@@ -655,11 +656,21 @@ SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
-    // same layout: these are slots this thread read in the last pass, no barrier needed before
-    if constexpr ((!C::SAME_LAYOUT || !LastExchangeSameAsTile<C>::value) && C::P > 1) plat::sync_block();
+    // same layout: these are slots this thread read in the last pass, no barrier needed before.  Otherwise a barrier is
+    // due anyway, and behind it the scratch may use ANY layout: linear, where the ascending writes and the descending
+    // partner reads are both conflict-free (a descending run collides 2-way with its wrapped lane under SW128)
+#if defined(SMFFT_EXP_TAIL_BARRIER)  // experiment: pay a barrier to get the linear scratch in the same-layout kernels too
+    constexpr bool EXTRA = C::SAME_LAYOUT && LastExchangeSameAsTile<C>::value && C::P > 1 && C::T >= 16 && C::E >= SMFFT_EXP_TAIL_BARRIER;
+#else
+    constexpr bool EXTRA = false;
+#endif
+    constexpr bool DUE = (!C::SAME_LAYOUT || !LastExchangeSameAsTile<C>::value) && C::P > 1;
+    constexpr bool FREE = (DUE || EXTRA) && C::T >= 16;
+    using TL = typename std::conditional<FREE, LayoutLinear, typename C::Layout>::type;
+    if constexpr (DUE || EXTRA) plat::sync_block();
     static_for<H>([&](auto II) {
         constexpr int m = H + decltype(II)::value;
-        plat::sts64(s + C::Layout::phys(fbase + t + m * C::T), v[m]);
+        plat::sts64(s + TL::phys(fbase + t + m * C::T), v[m]);
     });
     float2 wt;  // W_{2N}^t / 2
     if constexpr (C::TW == TW_LUT) {
@@ -676,7 +687,7 @@ SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
         const float2 Wh = mul_wconst<0, i, 2 * C::R>(wt);  // W_{2N}^{t + i T} / 2
         const float2 A = v[i];
         const int xb = (i == 0 && t == 0) ? fbase + C::N / 2 : fbase + C::N - t - i * C::T;
-        const float2 Bv = plat::lds64(s + C::Layout::phys(xb));
+        const float2 Bv = plat::lds64(s + TL::phys(xb));
         float2 lo, hi;
         r2c_pair<C::PACK>(A, Bv, Wh, lo, hi);
         if constexpr (i == 0) {

@@ -34,6 +34,14 @@ struct LayoutSW128H {
     static SMFFT_HOST_DEV int phys(int x) { return x ^ ((((x >> 4) & 7) ^ (((x >> 7) & 1) << 2)) << 1); }
 };
 
+// exchange layout after a radix-8 FIRST pass (reversed plans): 128-bit stores at x = 8j + q.  Eight consecutive virtual
+// threads cover four rows (two chunks each); keying on (row & 3) keeps them apart AND makes the layout periodic in four
+// rows, which is what the descending runs j' = 2T - t of the mirrored C2R ownership need: their wrapped lane lands on
+// the chunk the missing lane of the previous group would have used (SW128, periodic in eight rows, collides 2-way there)
+struct LayoutSW128Q {
+    static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 4) & 3) << 1); }
+};
+
 struct LayoutLinear {
     static SMFFT_HOST_DEV int phys(int x) { return x; }
 };
