@@ -659,15 +659,11 @@ SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
     // same layout: these are slots this thread read in the last pass, no barrier needed before.  Otherwise a barrier is
     // due anyway, and behind it the scratch may use ANY layout: linear, where the ascending writes and the descending
     // partner reads are both conflict-free (a descending run collides 2-way with its wrapped lane under SW128)
-#if defined(SMFFT_EXP_TAIL_BARRIER)  // experiment: pay a barrier to get the linear scratch in the same-layout kernels too
-    constexpr bool EXTRA = C::SAME_LAYOUT && LastExchangeSameAsTile<C>::value && C::P > 1 && C::T >= 16 && C::E >= SMFFT_EXP_TAIL_BARRIER;
-#else
-    constexpr bool EXTRA = false;
-#endif
+    // (paying an extra barrier for the linear scratch in the same-layout kernels loses 0.6-0.8 %, measured)
     constexpr bool DUE = (!C::SAME_LAYOUT || !LastExchangeSameAsTile<C>::value) && C::P > 1;
-    constexpr bool FREE = (DUE || EXTRA) && C::T >= 16;
+    constexpr bool FREE = DUE && C::T >= 16;
     using TL = typename std::conditional<FREE, LayoutLinear, typename C::Layout>::type;
-    if constexpr (DUE || EXTRA) plat::sync_block();
+    if constexpr (DUE) plat::sync_block();
     static_for<H>([&](auto II) {
         constexpr int m = H + decltype(II)::value;
         plat::sts64(s + TL::phys(fbase + t + m * C::T), v[m]);
