@@ -403,27 +403,36 @@ SMFFT_DEV void c2r_head_mirror(float2 (&v)[C::R], const float2* s, int fbase, in
 // ascending reads are whole 128-byte rows, and the descending mirror reads j' = Ns - t are conflict-free only there
 // (lane 0 wraps into column 0 of the next row, the one bank pair the other 15 lanes leave free).
 // Twiddles of the mirrored butterfly: W_N^{(Ns - t) q} = W_r^q conj(W_N^{t q});  thread 0: W_N^{T q} = W_{2r}^q.
+// With U > 2 butterflies per thread the same holds for U/2 pairs (a_i = t + iT, Ns - a_i).
 template <class C>
 struct MirrorR2C {
     static constexpr int PL = C::P - 1;
     static constexpr int r = 1 << C::radix_log2(PL);
-    static constexpr int NS = C::N / r;
-    static constexpr bool OK = !C::DUAL && C::P >= 3 && C::R == 16 && C::R / r == 2 && C::T >= 16 && C::VEC128 && C::REORDER == 1 &&
-                               (1 << C::ns_log2(C::P - 2)) >= 16 && std::is_same<typename C::Layout, LayoutSW128>::value;
-    // index (within the transform) of register m: even m = butterfly j = t, odd m = the mirror butterfly
-    static SMFFT_DEV int index(int t, int m) { return ((m & 1) ? (t == 0 ? C::T : NS - t) : t) + (m >> 1) * NS; }
+    static constexpr int U = C::R / r;   // butterflies per thread in the last pass = U/2 mirror pairs
+    static constexpr int NS = C::N / r;  // = U T virtual threads
+    // general U (even): pair i takes a_i = t + i T and its mirror Ns - a_i (the one self-mirrored slot a = 0 takes Ns/2)
+    static constexpr bool OK = !C::DUAL && C::P >= 3 && (C::R == 16 || C::R == 32) && U >= 2 && r >= 2 && C::T >= 16 && C::VEC128 &&
+                               C::REORDER == 1 && (1 << C::ns_log2(C::P - 2)) >= 16 && std::is_same<typename C::Layout, LayoutSW128>::value;
+    static SMFFT_DEV int vthread(int t, int u)
+    {
+        const int a = t + (u >> 1) * C::T;
+        return (u & 1) ? (a == 0 ? NS / 2 : NS - a) : a;
+    }
+    // index (within the transform) of register m = u + q U
+    static SMFFT_DEV int index(int t, int m) { return vthread(t, m % U) + (m / U) * NS; }
 };
 
 template <class C>
 SMFFT_DEV void load_mirror(float2 (&v)[C::R], const float2* s, int fbase, int t)
 {
     using M = MirrorR2C<C>;
-    const float2* a = s + fbase + t;
-    const float2* b = s + fbase + (t == 0 ? C::T : M::NS - t);
-    static_for<C::R / 2>([&](auto Q) {
-        constexpr int q = decltype(Q)::value;
-        v[2 * q] = plat::lds64(a + q * M::NS);
-        v[2 * q + 1] = plat::lds64(b + q * M::NS);
+    static_for<M::U>([&](auto UI) {
+        constexpr int u = decltype(UI)::value;
+        const float2* a = s + fbase + M::vthread(t, u);
+        static_for<M::r>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            v[u + q * M::U] = plat::lds64(a + q * M::NS);
+        });
     });
 }
 
@@ -431,21 +440,31 @@ template <class C>
 SMFFT_DEV void fft_pass_compute_mirror(float2 (&v)[C::R], int t, const float2* tw)
 {
     using M = MirrorR2C<C>;
-    constexpr int r = M::r;
+    constexpr int r = M::r, U = M::U, R = C::R;
     float2 pw[r];
     make_twiddle_powers<C::DIR, C::TW, C::N, r>(pw, t, tw + C::tw_offset(M::PL));
-    static_for<r>([&](auto QI) {
-        constexpr int q = decltype(QI)::value;
-        if constexpr (q >= 1) {
-            v[2 * q] = cmul(v[2 * q], pw[q]);
-            constexpr float cx = cos64(q * (64 / (2 * r))), sy = C::DIR ? sin64(q * (64 / (2 * r))) : -sin64(q * (64 / (2 * r)));
-            // conj of W_N^{t' q}, t' = t, or T for thread 0 (whose mirror butterfly is j' = T): W_N^{T q} = W_{2r}^q
-            const float2 wc = t == 0 ? make_float2(cx, -sy) : make_float2(pw[q].x, -pw[q].y);
-            v[2 * q + 1] = mul_wconst<C::DIR, q, r>(cmul(v[2 * q + 1], wc));
-        }
+    static_for<U / 2>([&](auto II) {
+        constexpr int i = decltype(II)::value;
+        static_for<r>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;
+            if constexpr (q >= 1) {
+                // a_i = t + i T:  W_N^{a q} = W_N^{t q} W_R^{i q}
+                v[2 * i + q * U] = mul_wconst<C::DIR, (i * q) % R, R>(cmul(v[2 * i + q * U], pw[q]));
+                // mirror Ns - a:  W_r^q conj(W_N^{a q}) = conj(W_N^{t q}) W_R^{qU - iq};  a = 0 (thread 0, pair 0) owns Ns/2
+                // instead: W_N^{(Ns/2) q} = W_{2r}^q = W_r^q conj(W_{2r}^q)
+                float2 wc = make_float2(pw[q].x, -pw[q].y);
+                if constexpr (i == 0) {
+                    constexpr float cx = cos64(q * (64 / (2 * r))), sy = C::DIR ? sin64(q * (64 / (2 * r))) : -sin64(q * (64 / (2 * r)));
+                    if (t == 0) wc = make_float2(cx, -sy);
+                }
+                v[2 * i + 1 + q * U] = mul_wconst<C::DIR, (((q * U - i * q) % R) + R) % R, R>(cmul(v[2 * i + 1 + q * U], wc));
+            }
+        });
     });
-    dft_regs<C::PACK, C::DIR, r, 0, 2, C::R>(v);
-    dft_regs<C::PACK, C::DIR, r, 1, 2, C::R>(v);
+    static_for<U>([&](auto UI) {
+        constexpr int u = decltype(UI)::value;
+        dft_regs<C::PACK, C::DIR, r, u, U, C::R>(v);
+    });
 }
 
 // one pair of the real pass: A = Z[k], Bv = Z[N-k], Wh = W_{2N}^k / 2  ->  lo = X[k], hi = X[N-k] (see r2c_tail_regs)
@@ -460,41 +479,50 @@ SMFFT_DEV void r2c_pair(float2 A, float2 Bv, float2 Wh, float2& lo, float2& hi)
 }
 
 // real pass on the mirrored ownership, registers only.  On return register m holds X[MirrorR2C::index(t, m)].
+// Pair i, butterfly 2i (a = t + iT), output q:  k = a + q Ns  <->  N - k = (Ns - a) + (r-1-q) Ns = butterfly 2i+1, output r-1-q;
+// W_{2N}^k = W_{2N}^t W_{2R}^{i + qU}.  The slot a = 0 (thread 0, pair 0) pairs within itself: k = q Ns <-> (r-q) Ns, bin 0
+// packs (X[0], X[N]), k = N/2 is its own partner; its sibling Ns/2 pairs k = Ns/2 + q Ns <-> Ns/2 + (r-1-q) Ns.
 template <class C>
 SMFFT_DEV void r2c_tail_mirror(float2 (&v)[C::R], const float2* tw)
 {
     using M = MirrorR2C<C>;
-    constexpr int r = M::r;
-    static_assert(4 * r <= 64, "constant twiddles of the mirrored real pass come from the W_64 table");
+    constexpr int r = M::r, U = M::U;
+    static_assert(4 * r <= 64 && 2 * C::R <= 64, "constant twiddles of the mirrored real pass come from the W_64 table");
     const int t = plat::tid() & (C::T - 1);
-    if (t != 0) {
-        float2 wt;  // W_{2N}^t / 2
-        if constexpr (C::TW == TW_LUT) {
-            wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
-        } else {
-            wt = tw_mufu<0, 2 * C::N>(t);
-            wt.x *= 0.5f;
-            wt.y *= 0.5f;
-        }
-        static_for<r>([&](auto QI) {
-            constexpr int q = decltype(QI)::value;  // k = t + q Ns, N - k = (Ns - t) + (r-1-q) Ns
-            r2c_pair<C::PACK>(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<0, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
-        });
+    float2 wt;  // W_{2N}^t / 2
+    if constexpr (C::TW == TW_LUT) {
+        wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
     } else {
-        // j = 0: k = q Ns pairs with (r-q) Ns; bin 0 packs (X[0], X[N]), k = N/2 is its own partner
-        const float2 z0 = v[0], zm = v[r];
+        wt = tw_mufu<0, 2 * C::N>(t);
+        wt.x *= 0.5f;
+        wt.y *= 0.5f;
+    }
+    auto general = [&](auto II) {
+        constexpr int i = decltype(II)::value;
+        static_for<r>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;
+            constexpr int ma = 2 * i + q * U, mb = 2 * i + 1 + (r - 1 - q) * U;
+            r2c_pair<C::PACK>(v[ma], v[mb], mul_wconst<0, i + q * U, 2 * C::R>(wt), v[ma], v[mb]);
+        });
+    };
+    static_for<U / 2>([&](auto II) {
+        if constexpr (decltype(II)::value >= 1) general(II);
+    });
+    if (t != 0) {
+        general(std::integral_constant<int, 0>{});
+    } else {
+        const float2 z0 = v[0], zm = v[(r / 2) * U];
         v[0] = make_float2(z0.x + z0.y, z0.x - z0.y);
-        v[r] = make_float2(zm.x, -zm.y);
+        v[(r / 2) * U] = make_float2(zm.x, -zm.y);
         static_for<r / 2>([&](auto QI) {
             constexpr int q = decltype(QI)::value;
             if constexpr (q >= 1)
-                r2c_pair<C::PACK>(v[2 * q], v[2 * (r - q)], mul_wconst<0, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
+                r2c_pair<C::PACK>(v[q * U], v[(r - q) * U], mul_wconst<0, q, 2 * r>(make_float2(0.5f, 0.0f)), v[q * U], v[(r - q) * U]);
         });
-        // j' = T: k = T + q Ns pairs with T + (r-1-q) Ns; W_{2N}^k = W_{4r}^{1 + 2q}
         static_for<r / 2>([&](auto QI) {
-            constexpr int q = decltype(QI)::value;
-            r2c_pair<C::PACK>(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<0, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
-                     v[2 * (r - 1 - q) + 1]);
+            constexpr int q = decltype(QI)::value;  // k = Ns/2 + q Ns:  W_{2N}^k = W_{4r}^{1 + 2q}
+            r2c_pair<C::PACK>(v[1 + q * U], v[1 + (r - 1 - q) * U], mul_wconst<0, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[1 + q * U],
+                              v[1 + (r - 1 - q) * U]);
         });
     }
 }

@@ -124,7 +124,7 @@ struct TuningReal<10> {
 template <>
 struct TuningReal<11> {
     static constexpr int B = 4, TILE_E = 11, F = 1, STAGES = 2, MINB = 6, CTAS = 6, PF = 1;
-    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+    static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;  // mirrored R2C: the descending half of the result leaves from registers
 };
 template <>
 struct TuningReal<12> {
@@ -162,6 +162,13 @@ struct ArithFor {
 #endif
 };
 
+// R2C of 8192 reals: the R = 32 plan [32,32,4] runs U = 8 butterflies per thread in its last pass, so the real pass owns
+// its pairs (MirrorR2C with four mirror pairs per thread): 1.59 -> 1.50 ms against the R = 16 shape, whose last pass has
+// U = 1.  (2048 reals: the same trick on [16,16,4] only ties with the single-exchange R = 32 shape, 1.332 vs 1.331 ms.)
+struct TuningR2C12 {
+    static constexpr int B = 5, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
 // (compute-bound: R = 32 pays at 512 and 1024 points, C2C 0.88 / 1.09 ms vs 1.12 / 1.13 ms, R2C 1.21 / 1.23 vs
 // 1.28 / 1.27 ms, not at 4096)
@@ -178,7 +185,9 @@ struct ShapeFor {
 #endif
                                                  (MODE != 0 && REPS > 1 && (E == 9 || E == 10)));
     static constexpr bool REAL = MODE != 0 && REPS == 1;
-    using type = typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type;
+    static constexpr bool M12 = MODE == 1 && REPS == 1 && E == 12;
+    using type = typename std::conditional<M12, TuningR2C12,
+                 typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type>::type;
 };
 
 }  // namespace kernels

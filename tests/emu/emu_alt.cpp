@@ -66,6 +66,10 @@ int emu_run_late(const void* in, void* out, int variant, long long n_ffts, int g
         case 13: return run_cfg<11, 4, 1, 0, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 4>(i, o, n_ffts, grid, nullptr);
         case 14: return run_cfg<11, 4, 1, 0, 1, 1, kernels::IO_LDG, TW_LUT, 1, 1, 0, 4>(i, o, n_ffts, grid, nullptr);
         case 15: return run_cfg<7, 4, 8, 0, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, -1, 4>(i, o, n_ffts, grid, nullptr);   // [8,16]
+        // mirrored R2C ownership with more than one butterfly pair per thread: U = 8 (R = 32, last radix 4), U = 8 (R = 16, last radix 2), U = 4
+        case 16: return run_cfg<12, 5, 1, 1, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 2>(i, o, n_ffts, grid, nullptr);
+        case 17: return run_cfg<9, 4, 4, 1, 0, 1, kernels::IO_TMA_STG, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);
+        case 18: return run_cfg<10, 4, 2, 1, 0, 1, kernels::IO_LDG, TW_MUFU, 1, 1, 0, 2>(i, o, n_ffts, grid, nullptr);
     }
     return -1;
 }

@@ -161,7 +161,8 @@ int emu_run(const void* in, void* out, int e, long long n_ffts, int mode, int di
         if (mode == 0 && reps == 1 && reorder == 1) return run_shape<E, Tq::B, Tq::F, 0, Tq::STAGES, 1, Tq::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         using Tr = kernels::ShapeFor<E, 1, 1, 1>::type; /* R2C / C2R shape */                                        \
         if (mode == 1 && reps == 1) return run_shape<E, Tr::B, Tr::F, 1, Tr::STAGES, 1, Tr::PF, kernels::ArithFor<E, 1, 1, 1>::value>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
-        if (mode == 2 && reps == 1) return run_shape<E, Tr::B, Tr::F, 2, Tr::STAGES, 1, Tr::PF, kernels::ArithFor<E, 2, 1, 1>::value>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
+        using Tc = kernels::ShapeFor<E, 2, 1, 1>::type; /* C2R shape */                                              \
+        if (mode == 2 && reps == 1) return run_shape<E, Tc::B, Tc::F, 2, Tc::STAGES, 1, Tc::PF, kernels::ArithFor<E, 2, 1, 1>::value>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 0 && reps == 1) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 1, Tn::PF>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
         if (mode == 0 && reps == 3) return run_shape<E, Tn::B, Tn::F, 0, Tn::STAGES, 3, -1, kernels::ArithFor<E, 0, 1, 100>::value>(i, o, n_ffts, dir, reorder, io, tw, grid, bank_factor); \
     }
