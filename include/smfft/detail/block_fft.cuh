@@ -58,7 +58,7 @@ struct BlockCfg {
     static constexpr int PACK = (DUAL_ >> 1) & 1;  // one transform per thread, packed (re, im) add / subtract in the butterflies
     static constexpr int REV = (DUAL_ >> 2) & 1;   // pass plan with the small radix FIRST: [2^(E mod B), R, .., R]
     static constexpr int THREADS = (F_ * T) >> DUAL;
-    static_assert(DUAL_ >= 0 && DUAL_ < 8 && (!REV || (E_ % B_ == 3 && VEC128_)), "reversed plans: first radix 8 only");
+    static_assert(DUAL_ >= 0 && DUAL_ < 8 && (!REV || ((E_ % B_ == 3 || E_ % B_ == 2) && VEC128_)), "reversed plans: first radix 8 or 4");
     static_assert((DUAL_ & 1) == 0 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
                                  std::is_same<Layout_, LayoutSW128>::value && VEC128_),
                   "dual-lane transforms: an even number of transforms per tile, T >= 16, N >= 128, R >= 16, SW128 tile");
@@ -147,7 +147,8 @@ template <class C, class LY = typename C::Layout>
 SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t)
 {
     using NA = NaturalAccess<C, LY>;
-    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value && !std::is_same<LY, LayoutSW128H>::value) {
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value && !std::is_same<LY, LayoutSW128H>::value &&
+                  !std::is_same<LY, LayoutSW128R4>::value) {
         const int p0 = LY::phys(fbase + t);  // bits 4..6 do not depend on m
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
@@ -176,7 +177,8 @@ template <class C, class LY = typename C::Layout>
 SMFFT_DEV void store_natural(const float2 (&v)[C::R], float2* s, int fbase, int t)
 {
     using NA = NaturalAccess<C, LY>;
-    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value && !std::is_same<LY, LayoutSW128H>::value) {
+    if constexpr (C::T % 128 == 0 && C::N % 128 == 0 && !std::is_same<LY, LayoutSW256>::value && !std::is_same<LY, LayoutSW128H>::value &&
+                  !std::is_same<LY, LayoutSW128R4>::value) {
         const int p0 = LY::phys(fbase + t);
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
@@ -262,14 +264,20 @@ SMFFT_DEV void fft_pass_compute(float2 (&v)[C::R], int vt, const float2* tw)
     });
 }
 
+template <class C>
+struct MirrorC2R;
+
 template <class C, int PIDX, class XL = typename C::XLayout>
-SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, int vt, int j1 = -1)
+SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, int vt, bool mirror_c2r = false)
 {
     constexpr int c = C::radix_log2(PIDX), r = 1 << c, U = C::R / r;
     constexpr int LNS = C::ns_log2(PIDX), NS = 1 << LNS;
     static_for<U>([&](auto UI) {
         constexpr int u = decltype(UI)::value;
-        const int j = (u == 1 && j1 >= 0) ? j1 : vt + u * C::T;  // j1: virtual thread of butterfly 1 (mirrored ownership)
+        int j = vt + u * C::T;
+        if constexpr (PIDX == 0 && U >= 2) {
+            if (mirror_c2r) j = MirrorC2R<C>::vthread(vt, u);  // mirrored ownership of the C2R first pass
+        }
         const int xb = fbase + ((j >> LNS) << (LNS + c)) + (j & (NS - 1));
         if constexpr (NS == 1 && C::VEC128) {
             // r contiguous outputs per butterfly: 128-bit stores
@@ -314,9 +322,13 @@ SMFFT_DEV HookAt<PASS_, F> hook_at(F f)
 // layout of the exchange that follows pass PIDX
 template <class C, int PIDX>
 struct ExchangeLayout {
+    static constexpr bool SW = std::is_same<typename C::Layout, LayoutSW128>::value;
     static constexpr bool H = C::ns_log2(PIDX) == 3 && std::is_same<typename C::XLayout, LayoutSW128>::value;
     static constexpr bool Q = C::REV && PIDX == 0 && C::radix_log2(0) == 3 && std::is_same<typename C::XLayout, LayoutSW128>::value;
-    using type = typename std::conditional<H, LayoutSW128H, typename std::conditional<Q, LayoutSW128Q, typename C::XLayout>::type>::type;
+    static constexpr bool P2 = C::REV && SW && PIDX == 0 && C::radix_log2(0) == 2;   // radix-4 first pass
+    static constexpr bool R4 = C::REV && SW && C::ns_log2(PIDX) == 2 && PIDX >= 1;   // the Ns = 4 exchange after it
+    using type = typename std::conditional<P2, LayoutSW128P, typename std::conditional<R4, LayoutSW128R4,
+                 typename std::conditional<H, LayoutSW128H, typename std::conditional<Q, LayoutSW128Q, typename C::XLayout>::type>::type>::type>::type;
 };
 // the layout the LAST pass reads from = where the in-place result must not be written without a barrier
 template <class C>
@@ -332,10 +344,15 @@ struct LastExchangeSameAsTile {
 template <class C>
 struct MirrorC2R {
     static constexpr int r = 1 << C::radix_log2(0);
-    static constexpr int NS2 = C::N / r;  // = 2T
-    static constexpr bool OK = !C::DUAL && C::REV && C::P >= 2 && C::R == 16 && C::R / r == 2 && C::T >= 16 && C::VEC128 &&
+    static constexpr int U = C::R / r;    // butterflies per thread in the first pass = U/2 mirror pairs
+    static constexpr int NS2 = C::N / r;  // = U T virtual threads
+    static constexpr bool OK = !C::DUAL && C::REV && C::P >= 2 && (C::R == 16 || C::R == 32) && U >= 2 && r >= 4 && C::T >= 16 && C::VEC128 &&
                                C::REORDER == 1 && std::is_same<typename C::Layout, LayoutSW128>::value;
-    static SMFFT_DEV int mirror_j(int t) { return t == 0 ? C::T : NS2 - t; }
+    static SMFFT_DEV int vthread(int t, int u)
+    {
+        const int a = t + (u >> 1) * C::T;
+        return (u & 1) ? (a == 0 ? NS2 / 2 : NS2 - a) : a;
+    }
 };
 
 // one pair of the inverse real pass: A = Y[k], Bv = Y[N-k], Wh = exp(+2 pi i k / 2N) / 2  ->  zk = Z[k], zn = Z[N-k]
@@ -350,45 +367,56 @@ SMFFT_DEV void c2r_pair(float2 A, float2 Bv, float2 Wh, float2& zk, float2& zn)
     zn = make_float2(0.5f * sx + p, -0.5f * dy - q);
 }
 
-// v[2q] = Y[t + q 2T], v[2q+1] = Y[j' + q 2T] from the (read-only, SW128) tile, then the inverse real pass on the pairs
+// v[u + qU] = Y[vthread(t, u) + q Ns] from the (read-only, SW128) tile, then the inverse real pass on the pairs
+// (pair i: butterfly 2i output q  <->  butterfly 2i+1 output r-1-q; the slot a = 0 pairs within itself, see r2c_tail_mirror)
 template <class C>
 SMFFT_DEV void c2r_head_mirror(float2 (&v)[C::R], const float2* s, int fbase, int t, const float2* tw)
 {
     using M = MirrorC2R<C>;
-    constexpr int r = M::r;
-    static_assert(4 * r <= 64, "constant twiddles of the mirrored real pass come from the W_64 table");
-    const int jm = M::mirror_j(t);
-    static_for<r>([&](auto QI) {
-        constexpr int q = decltype(QI)::value;
-        v[2 * q] = plat::lds64(s + C::Layout::phys(fbase + t + q * M::NS2));
-        v[2 * q + 1] = plat::lds64(s + C::Layout::phys(fbase + jm + q * M::NS2));
+    constexpr int r = M::r, U = M::U;
+    static_assert(4 * r <= 64 && 2 * C::R <= 64, "constant twiddles of the mirrored real pass come from the W_64 table");
+    static_for<U>([&](auto UI) {
+        constexpr int u = decltype(UI)::value;
+        const int j = M::vthread(t, u);
+        static_for<r>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;
+            v[u + q * U] = plat::lds64(s + C::Layout::phys(fbase + j + q * M::NS2));
+        });
+    });
+    float2 wt;  // exp(+2 pi i t / 2N) / 2
+    if constexpr (C::TW == TW_LUT) {
+        wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
+    } else {
+        wt = tw_mufu<1, 2 * C::N>(t);
+        wt.x *= 0.5f;
+        wt.y *= 0.5f;
+    }
+    auto general = [&](auto II) {
+        constexpr int i = decltype(II)::value;
+        static_for<r>([&](auto QI) {
+            constexpr int q = decltype(QI)::value;
+            constexpr int ma = 2 * i + q * U, mb = 2 * i + 1 + (r - 1 - q) * U;
+            c2r_pair<C::PACK>(v[ma], v[mb], mul_wconst<1, i + q * U, 2 * C::R>(wt), v[ma], v[mb]);
+        });
+    };
+    static_for<U / 2>([&](auto II) {
+        if constexpr (decltype(II)::value >= 1) general(II);
     });
     if (t != 0) {
-        float2 wt;  // exp(+2 pi i t / 2N) / 2
-        if constexpr (C::TW == TW_LUT) {
-            wt = plat::lds64(tw + C::TW_C2C_ENTRIES + t);
-        } else {
-            wt = tw_mufu<1, 2 * C::N>(t);
-            wt.x *= 0.5f;
-            wt.y *= 0.5f;
-        }
-        static_for<r>([&](auto QI) {
-            constexpr int q = decltype(QI)::value;  // k = t + q 2T, N - k = (2T - t) + (r-1-q) 2T
-            c2r_pair<C::PACK>(v[2 * q], v[2 * (r - 1 - q) + 1], mul_wconst<1, q, 2 * r>(wt), v[2 * q], v[2 * (r - 1 - q) + 1]);
-        });
+        general(std::integral_constant<int, 0>{});
     } else {
-        const float2 y0 = v[0], ym = v[r];
+        const float2 y0 = v[0], ym = v[(r / 2) * U];
         v[0] = make_float2(0.5f * (y0.x + y0.y), 0.5f * (y0.x - y0.y));  // bin 0 un-packed (RC:280-286)
-        v[r] = make_float2(ym.x, -ym.y);                                 // k = N/2 is its own partner
+        v[(r / 2) * U] = make_float2(ym.x, -ym.y);                       // k = N/2 is its own partner
         static_for<r / 2>([&](auto QI) {
             constexpr int q = decltype(QI)::value;
             if constexpr (q >= 1)
-                c2r_pair<C::PACK>(v[2 * q], v[2 * (r - q)], mul_wconst<1, q, 2 * r>(make_float2(0.5f, 0.0f)), v[2 * q], v[2 * (r - q)]);
+                c2r_pair<C::PACK>(v[q * U], v[(r - q) * U], mul_wconst<1, q, 2 * r>(make_float2(0.5f, 0.0f)), v[q * U], v[(r - q) * U]);
         });
         static_for<r / 2>([&](auto QI) {
-            constexpr int q = decltype(QI)::value;  // k = T + q 2T
-            c2r_pair<C::PACK>(v[2 * q + 1], v[2 * (r - 1 - q) + 1], mul_wconst<1, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[2 * q + 1],
-                     v[2 * (r - 1 - q) + 1]);
+            constexpr int q = decltype(QI)::value;  // k = Ns/2 + q Ns
+            c2r_pair<C::PACK>(v[1 + q * U], v[1 + (r - 1 - q) * U], mul_wconst<1, 1 + 2 * q, 4 * r>(make_float2(0.5f, 0.0f)), v[1 + q * U],
+                              v[1 + (r - 1 - q) * U]);
         });
     }
 }
@@ -548,7 +576,7 @@ SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t
             load_mirror<C>(v, s, fbase, t);
         } else {
             if constexpr (XF == 2 /* XF_C2R */ && MirrorC2R<C>::OK && PIDX == 0)
-                fft_pass_scatter<C, PIDX, XL>(v, s, fbase, vt, MirrorC2R<C>::mirror_j(t));
+                fft_pass_scatter<C, PIDX, XL>(v, s, fbase, vt, true);
             else
                 fft_pass_scatter<C, PIDX, XL>(v, s, fbase, vt);
             plat::sync_block();

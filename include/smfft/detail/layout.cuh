@@ -42,6 +42,18 @@ struct LayoutSW128Q {
     static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 4) & 3) << 1); }
 };
 
+// reversed plans with a radix-4 first pass: 128-bit stores at x = 4j + q put eight consecutive virtual threads on the
+// even chunks of two rows; keying on (row & 1) separates the rows and is periodic in two rows (the descending mirror runs
+// need the periodicity, as in LayoutSW128Q)
+struct LayoutSW128P {
+    static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 4) & 1) << 1); }
+};
+// ... and the Ns = 4 exchange that follows: sixteen consecutive virtual threads write the same four columns of four rows
+// that are eight rows apart; bits 7..8 of x select the quarter of the row
+struct LayoutSW128R4 {
+    static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 7) & 3) << 2); }
+};
+
 struct LayoutLinear {
     static SMFFT_HOST_DEV int phys(int x) { return x; }
 };

@@ -156,7 +156,7 @@ struct ArithFor {
     static constexpr int value = SMFFT_FORCE_ARITH;
 #else
     static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : 2)
-                                 : (MODE == 2 && E == 11) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
+                                 : (MODE == 2 && (E == 11 || E == 12)) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
                                  : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2
                                  : (MODE == 0 && (E == 11 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans, sustained load
 #endif
@@ -166,6 +166,12 @@ struct ArithFor {
 // its pairs (MirrorR2C with four mirror pairs per thread): 1.59 -> 1.50 ms against the R = 16 shape, whose last pass has
 // U = 1.  (2048 reals: the same trick on [16,16,4] only ties with the single-exchange R = 32 shape, 1.332 vs 1.331 ms.)
 struct TuningR2C12 {
+    static constexpr int B = 5, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+// C2R of 8192 reals: the mirror image, reversed R = 32 plan [4,32,32] (MirrorC2R with four mirror pairs per thread):
+// 1.59 -> 1.49 ms.  (2048 reals on the reversed R = 16 plan [4,16,16] loses to the single-exchange shape, 1.39-1.44 vs 1.35 ms.)
+struct TuningC2R12 {
     static constexpr int B = 5, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
@@ -186,8 +192,9 @@ struct ShapeFor {
                                                  (MODE != 0 && REPS > 1 && (E == 9 || E == 10)));
     static constexpr bool REAL = MODE != 0 && REPS == 1;
     static constexpr bool M12 = MODE == 1 && REPS == 1 && E == 12;
-    using type = typename std::conditional<M12, TuningR2C12,
-                 typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type>::type;
+    static constexpr bool C12 = MODE == 2 && REPS == 1 && E == 12;
+    using type = typename std::conditional<M12, TuningR2C12, typename std::conditional<C12, TuningC2R12,
+                 typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type>::type>::type;
 };
 
 }  // namespace kernels

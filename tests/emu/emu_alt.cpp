@@ -70,6 +70,11 @@ int emu_run_late(const void* in, void* out, int variant, long long n_ffts, int g
         case 16: return run_cfg<12, 5, 1, 1, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 2>(i, o, n_ffts, grid, nullptr);
         case 17: return run_cfg<9, 4, 4, 1, 0, 1, kernels::IO_TMA_STG, TW_LUT, 2, 1, 1>(i, o, n_ffts, grid, nullptr);
         case 18: return run_cfg<10, 4, 2, 1, 0, 1, kernels::IO_LDG, TW_MUFU, 1, 1, 0, 2>(i, o, n_ffts, grid, nullptr);
+        // reversed plans with a radix-4 first pass: [4,32,32] C2C and mirrored C2R (U = 8), [4,16,16] mirrored C2R (U = 4)
+        case 19: return run_cfg<12, 5, 1, 0, 0, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 4>(i, o, n_ffts, grid, nullptr);
+        case 20: return run_cfg<12, 5, 1, 2, 1, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 6>(i, o, n_ffts, grid, nullptr);
+        case 21: return run_cfg<10, 4, 2, 2, 1, 1, kernels::IO_TMA_STG, TW_LUT, 2, 1, 1, 6>(i, o, n_ffts, grid, nullptr);
+        case 22: return run_cfg<10, 4, 1, 0, 1, 1, kernels::IO_LDG, TW_MUFU, 1, 1, 0, 4>(i, o, n_ffts, grid, nullptr);
     }
     return -1;
 }
