@@ -154,6 +154,13 @@ SMFFT_DEV void load_natural(float2 (&v)[C::R], const float2* s, int fbase, int t
             constexpr int m = decltype(M)::value;
             v[m] = plat::lds64(s + p0 + m * C::T);
         });
+    } else if constexpr (C::T == 128 && C::N % 256 == 0 && std::is_same<LY, LayoutSW128H>::value) {
+        // the key depends on m only through bit 7 of x = t + m*128, i.e. on the parity of m: two bases, constant offsets
+        const int pe = LY::phys(fbase + t), po = LY::phys(fbase + t + C::T) - C::T;
+        static_for<C::R>([&](auto M) {
+            constexpr int m = decltype(M)::value;
+            v[m] = plat::lds64(s + ((m & 1) ? po : pe) + m * C::T);
+        });
     } else if constexpr (NA::SKEW) {
         const int sk = NA::skew(fbase);
         float2 a[C::R];
@@ -286,6 +293,14 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
                 const float2 lo = v[u + q * U], hi = v[u + (q + 1) * U];
                 plat::sts128(s + XL::phys(xb + q), make_float4(lo.x, lo.y, hi.x, hi.y));
             });
+        } else if constexpr (NS == 8 && r == 16 && std::is_same<XL, LayoutSW128H>::value) {
+            // x = xb + 8q without carries (xb holds bits 0..2 and 7.., 8q bits 3..6): the SW128H key of x is
+            // ((q >> 1) & 7) ^ (bit 7 of xb << 2), so phys(x) = (xb ^ (bit7 << 3)) ^ (8q ^ (((q >> 1) & 7) << 1)): one XOR per store
+            const int bq = xb ^ (((xb >> 7) & 1) << 3);
+            static_for<r>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                plat::sts64(s + (bq ^ ((8 * q) ^ (((q >> 1) & 7) << 1))), v[u + q * U]);
+            });
         } else if constexpr (NS % 256 == 0) {
             const int p0 = XL::phys(xb);  // q*NS leaves bits 0..7 alone (SW128 keys on bits 4..6, SW256 on 5..7)
             static_for<r>([&](auto QI) {
@@ -378,10 +393,18 @@ SMFFT_DEV void c2r_head_mirror(float2 (&v)[C::R], const float2* s, int fbase, in
     static_for<U>([&](auto UI) {
         constexpr int u = decltype(UI)::value;
         const int j = M::vthread(t, u);
-        static_for<r>([&](auto QI) {
-            constexpr int q = decltype(QI)::value;
-            v[u + q * U] = plat::lds64(s + C::Layout::phys(fbase + j + q * M::NS2));
-        });
+        if constexpr (M::NS2 % 128 == 0) {
+            const int p = C::Layout::phys(fbase + j);  // q*Ns moves whole groups of eight rows: the swizzle key stays
+            static_for<r>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                v[u + q * U] = plat::lds64(s + p + q * M::NS2);
+            });
+        } else {
+            static_for<r>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                v[u + q * U] = plat::lds64(s + C::Layout::phys(fbase + j + q * M::NS2));
+            });
+        }
     });
     float2 wt;  // exp(+2 pi i t / 2N) / 2
     if constexpr (C::TW == TW_LUT) {
@@ -757,7 +780,17 @@ SMFFT_DEV void r2c_tail_regs(float2 (&v)[C::R], float2* s, const float2* tw)
 template <class C, int XF>
 SMFFT_DEV void store_result(const float2 (&v)[C::R], float2* s, int fbase, int t)
 {
-    if constexpr (XF == XF_R2C) {
+    if constexpr (XF == XF_R2C && MirrorR2C<C>::OK && MirrorR2C<C>::NS % 128 == 0) {
+        using M = MirrorR2C<C>;  // q*Ns moves whole groups of eight rows: one swizzled base per butterfly, constant offsets
+        static_for<M::U>([&](auto UI) {
+            constexpr int u = decltype(UI)::value;
+            const int p = C::Layout::phys(fbase + M::vthread(t, u));
+            static_for<M::r>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                plat::sts64(s + p + q * M::NS, v[u + q * M::U]);
+            });
+        });
+    } else if constexpr (XF == XF_R2C) {
         static_for<C::R>([&](auto M) {
             constexpr int m = decltype(M)::value;
             plat::sts64(s + C::Layout::phys(fbase + r2c_out_index<C>(t, m)), v[m]);
