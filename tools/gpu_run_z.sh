@@ -11,7 +11,7 @@ echo "=== ncu launch list (bench)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/ncu_launches_zz.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-baselines --no-other-modes > gpurun_out/ncu_bench_zz.log 2>&1; echo "rc=$?"
 echo "=== ncu full"
 mkdir -p /tmp/ncu
-for cfg in "c2c 1024 1" "c2c 2048 1" "c2c 4096 1" "c2c 4096 0" "c2c 32 1" "c2c 128 1" "r2c 4096 1" "c2r 4096 1" "r2c 2048 1" "multiple 1024 1" "multiple 2048 1"; do set -- $cfg
+for cfg in "c2c 1024 1" "c2c 2048 1" "c2c 4096 1" "c2c 32 1" "c2c 128 1" "r2c 4096 1" "c2r 4096 1" "r2c 8192 1" "c2r 8192 1" "r2c 2048 1" "multiple 1024 1" "multiple 2048 1"; do set -- $cfg
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:smfft_tile_kernel -s 2 -c 1 -f -o /tmp/ncu/prof_z_$1_n$2_r$3 python tools/ncu_target.py $1 $2 $3 > gpurun_out/ncu_full_zz_$1_$2_$3.log 2>&1; echo "ncu full $1 $2 $3 rc=$?"
 done
 python tools/ncu_summarize.py gpurun_out/ncu_summary_zz.md /tmp/ncu/prof_z_*.ncu-rep > gpurun_out/ncu_summarize_zz.log 2>&1; echo "summarize rc=$?"
