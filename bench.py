@@ -58,7 +58,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index: int):
         self.index = index
@@ -72,7 +72,18 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t_begin=None, t_end=None):
+        """the sampler is started early (nvidia-smi needs a few hundred ms to come up on an 8-GPU box); samples are kept
+        when their timestamp falls inside [t_begin, t_end] (the timed region), all of them if that leaves nothing"""
         if self.p is not None:
             time.sleep(0.06)
             self.p.terminate()
@@ -89,20 +100,22 @@ class ClockSampler:
                                       capture_output=True, text=True, timeout=20).stdout
             except Exception:
                 text = ""
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in text.splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
+                rows.append((self._epoch(c[9]) if len(c) > 9 else None, float(c[1]), float(c[2]),
+                             [name for name, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        if t_begin is not None and t_end is not None:
+            inside = [r for r in rows if r[0] is not None and t_begin - 0.03 <= r[0] <= t_end + 0.03]
+            if inside:
+                rows = inside
+        sm, mx, reasons = [r[1] for r in rows], [r[2] for r in rows], set(x for r in rows for x in r[3])
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -319,22 +332,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = sm.launch_count()
     rec = []
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall_begin = time.time()
     t0.record()
     for _ in range(args.steps):
         step(rec)
     t1.record()
     barrier()
+    wall_end = time.time()
     launches = sm.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall_begin, wall_end)
     ms_total = t0.elapsed_time(t1)
     step_bytes = len(cfgs) * BATCH_POINTS * BYTES_PER_POINT
     tmax, units = reduce_job(torch.tensor([ms_total], dtype=torch.float64, device="cuda"),
