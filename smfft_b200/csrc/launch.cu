@@ -32,6 +32,7 @@ static int g_opt_io = 0;  // 0 auto (measured best TMA staging per size), 1 LDG,
 static int g_opt_tw = TW_LUT;
 static int g_opt_quirk4096 = 0;
 static int g_opt_ctas_per_sm = 0;
+static int g_opt_carveout = -2;  // -2: per kernel (see launch_batch), -1: driver default, 0..100: percent of shared memory
 static cudaStream_t g_stream = 0;
 static long long g_launches = 0;
 
@@ -143,7 +144,8 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     for (const void* f : ds->attr_done) need_attr &= (f != k->func);
     if (need_attr) {
         CUDA_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, k->smem_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      g_opt_carveout >= -1 ? g_opt_carveout : (int)cudaSharedmemCarveoutMaxShared));
         ds->attr_done.push_back(k->func);
     }
     kernels::TileArgs args;
@@ -258,6 +260,13 @@ int smfft_set_option(const char* key, int value)
     if (!strcmp(key, "twiddle")) { if (value < 0 || value > 1) return fail("twiddle must be 0 or 1"); g_opt_tw = value; return 0; }
     if (!strcmp(key, "quirk_4096")) { g_opt_quirk4096 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
+    if (!strcmp(key, "carveout")) {  // experiment switch: takes effect for kernels not launched yet (or after a new process)
+        if (value < -2 || value > 100) return fail("carveout must be -2 (per kernel), -1 (driver default) or 0..100");
+        g_opt_carveout = value;
+        DeviceState* ds = nullptr;
+        if (!get_device_state(&ds)) ds->attr_done.clear();
+        return 0;
+    }
     return fail("smfft: unknown option '%s'", key);
 }
 
@@ -267,6 +276,7 @@ int smfft_get_option(const char* key)
     if (!strcmp(key, "twiddle")) return g_opt_tw;
     if (!strcmp(key, "quirk_4096")) return g_opt_quirk4096;
     if (!strcmp(key, "ctas_per_sm")) return g_opt_ctas_per_sm;
+    if (!strcmp(key, "carveout")) return g_opt_carveout;
     if (!strcmp(key, "device_sms")) { DeviceState* ds = nullptr; return get_device_state(&ds) ? -1 : ds->sms; }
     return -1;
 }

@@ -58,6 +58,20 @@ void add_sizes_reg_b() {}
 void add_sizes_reg_d() {}
 void add_sizes_reg_e() {}
 #endif
+#ifdef TUNE_ONLY_REG  // only the register-direct sweep is linked
+void add_sizes_a() {}
+void add_sizes_b() {}
+void add_sizes_c() {}
+void add_sizes_d() {}
+void add_sizes_real_a() {}
+void add_sizes_real_b() {}
+void add_sizes_real_c() {}
+void add_sizes_dual_a() {}
+void add_sizes_dual_b() {}
+void add_sizes_dual_c() {}
+void add_sizes_dual_d() {}
+void add_sizes_dual_e() {}
+#endif
 #ifdef TUNE_ONLY_DUAL  // only the dual-lane sweep is linked
 void add_sizes_a() {}
 void add_sizes_b() {}
@@ -174,7 +188,12 @@ int main(int argc, char** argv)
         if (only_e && k.e != only_e) continue;
         cudaFuncAttributes fa;
         if (cudaFuncSetAttribute(k.func, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes) != cudaSuccess) { cudaGetLastError(); continue; }
-        cudaFuncSetAttribute(k.func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        {
+            // TUNE_CARVEOUT: shared-memory carve-out in percent (100 = max shared, the product setting for the TMA kernels;
+            // -1 = driver default).  The LDG/STG paths want the L1 that a small carve-out leaves (tools/fftlike_copy.cu)
+            const char* cv = getenv("TUNE_CARVEOUT");
+            cudaFuncSetAttribute(k.func, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
+        }
         CK(cudaFuncGetAttributes(&fa, k.func));
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.func, k.threads, k.smem_bytes));
