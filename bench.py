@@ -434,7 +434,7 @@ def run_ours(args):
         "config": {"workload": "CT C2C forward, N=32..4096 x {reorder, no-reorder}: 16 FFT_external launches per step, 4 GiB float2 batch per GPU (BASELINE.json configs[1])",
                    "batch_bytes_in": BATCH_POINTS * 8, "l2": "inputs (4 GiB) larger than L2 (126 MB); no flush needed",
                    "sharding": f"batch-sharded x{world}, no data-path collective",
-                   "io": {0: "tma (auto)", 1: "ldg", 2: "tma", 3: "tma_stg"}[sm.get_option("io")], "twiddle": "lut" if sm.get_option("twiddle") == 0 else "mufu"},
+                   "io": {0: "auto (measured best staging per size)", 1: "ldg", 2: "tma", 3: "tma_stg", 4: "reg"}[sm.get_option("io")], "twiddle": "lut" if sm.get_option("twiddle") == 0 else "mufu"},
         "ms_per_4GiB_batch": avg_launch_ms,
         "per_size": per_size,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -91,10 +91,12 @@ int smfft_pipeline_host(const void* h_in, void* h_out, int fft_size, long long n
 
 /* ---- knobs -------------------------------------------------------------------------------------
  * keys: "io" (0 = measured best TMA staging per size [default], 1 = LDG/STG staging by the threads,
- * 2 = TMA loads + TMA stores, 3 = TMA loads + stores from registers), "twiddle" (0 = table+powers
+ * 2 = TMA loads + TMA stores, 3 = TMA loads + stores from registers, 4 = register-direct input where an instance
+ * exists [1024-point natural-order C2C], the default elsewhere), "twiddle" (0 = table+powers
  * [default], 1 = MUFU __sincosf), "quirk_4096" (1 = reproduce FFT_4096_inverse_noreorder running
  * the forward transform, CT/SM_FFT_parameters.cuh:388; default 0 = mathematically correct),
- * "ctas_per_sm" (0 = built-in), "device_sms" (read-only). */
+ * "ctas_per_sm" (0 = built-in), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
+ * of shared memory), "device_sms" (read-only). */
 int smfft_set_option(const char* key, int value);
 int smfft_get_option(const char* key);
 /* CUDA stream (cudaStream_t as void*) used for launches and event timing; NULL = legacy default */

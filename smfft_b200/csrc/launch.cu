@@ -132,10 +132,12 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     if (n_points <= 0) return 0;
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail("smfft: device pointers must be 16-byte aligned");
     int io = reps > 1 ? kernels::IO_LDG
-                      : g_opt_io == 0 ? -1 : g_opt_io == 1 ? kernels::IO_LDG : g_opt_io == 2 ? kernels::IO_TMA : kernels::IO_TMA_STG;
+                      : g_opt_io == 0 ? -1 : g_opt_io == 1 ? kernels::IO_LDG : g_opt_io == 2 ? kernels::IO_TMA
+                      : g_opt_io == 3 ? kernels::IO_TMA_STG : kernels::IO_REG;
     const KernelEntry* k = find_entry(mode, e, dir, reorder, io, g_opt_tw, reps);
+    if (!k && io == kernels::IO_REG) k = find_entry(mode, e, dir, reorder, -1, g_opt_tw, reps);  // no register-direct instance: the default one
     if (!k && io == kernels::IO_TMA_STG) k = find_entry(mode, e, dir, reorder, kernels::IO_TMA, g_opt_tw, reps);
-    if (k && k->io != kernels::IO_LDG && n_points < k->tile_points)  // batch smaller than one tile: thread staging, no tensor map
+    if (k && kernels::io_uses_tma(k->io) && n_points < k->tile_points)  // batch smaller than one tile: thread staging, no tensor map
         k = find_entry(mode, e, dir, reorder, kernels::IO_LDG, g_opt_tw, reps);
     if (k) io = k->io;
     if (!k) return fail("smfft: no kernel instance for mode %d, 2^%d points, dir %d, reorder %d, io %d, tw %d, reps %d", mode, e, dir, reorder, io, g_opt_tw, reps);
@@ -144,8 +146,10 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     for (const void* f : ds->attr_done) need_attr &= (f != k->func);
     if (need_attr) {
         CUDA_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, k->smem_bytes));
-        CUDA_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      g_opt_carveout >= -1 ? g_opt_carveout : (int)cudaSharedmemCarveoutMaxShared));
+        // TMA kernels: max shared (their loads bypass L1, a smaller carve-out only costs occupancy).  Register-direct kernels:
+        // the driver's default, which leaves the large L1 their LDG/STG traffic needs ("cuFFT's 1.22 ms")
+        const int carve = k->io == kernels::IO_REG ? (int)cudaSharedmemCarveoutDefault : (int)cudaSharedmemCarveoutMaxShared;
+        CUDA_TRY(cudaFuncSetAttribute(k->func, cudaFuncAttributePreferredSharedMemoryCarveout, g_opt_carveout >= -1 ? g_opt_carveout : carve));
         ds->attr_done.push_back(k->func);
     }
     kernels::TileArgs args;
@@ -155,7 +159,7 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     args.gin = (const float2*)d_in;
     args.gout = (float2*)d_out;
     args.tw = ds->tw;
-    if (io != kernels::IO_LDG) {
+    if (kernels::io_uses_tma(io)) {
         if (make_map(&args.in_map, d_in, n_points / 16, k->tile_points / 16)) return 1;
         if (io == kernels::IO_TMA && make_map(&args.out_map, d_out, n_points / 16, k->tile_points / 16)) return 1;
     }
@@ -167,7 +171,9 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     int per_sm = g_opt_ctas_per_sm > 0 ? g_opt_ctas_per_sm : (k->ctas > 0 ? k->ctas : fit);
     if (per_sm > fit) per_sm = fit;
     long long grid = (long long)ds->sms * per_sm;
+    if (k->ctas < 0 && g_opt_ctas_per_sm <= 0) grid = args.n_tiles;  // one CTA per tile
     if (grid > args.n_tiles) grid = args.n_tiles;
+    if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;  // the kernels stride over the tiles, any grid is correct
     void* params[] = {&args};
     CUDA_TRY(cudaLaunchKernel(k->func, dim3((unsigned)grid), dim3((unsigned)k->threads), params, (size_t)k->smem_bytes, g_stream));
     g_launches++;
@@ -256,7 +262,7 @@ int smfft_set_stream(void* stream)
 
 int smfft_set_option(const char* key, int value)
 {
-    if (!strcmp(key, "io")) { if (value < 0 || value > 3) return fail("io must be 0..3"); g_opt_io = value; return 0; }
+    if (!strcmp(key, "io")) { if (value < 0 || value > 4) return fail("io must be 0..4"); g_opt_io = value; return 0; }
     if (!strcmp(key, "twiddle")) { if (value < 0 || value > 1) return fail("twiddle must be 0 or 1"); g_opt_tw = value; return 0; }
     if (!strcmp(key, "quirk_4096")) { g_opt_quirk4096 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }

@@ -52,6 +52,18 @@ KernelEntry make_entry()
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
     constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
     k.prefer = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);
+    if (kernels::RegDirect<E>::ON && kernels::RegDirect<E>::PREFER && MODE == kernels::MODE_C2C && REORDER == 1 && REPS == 1) k.prefer = 0;
+    return k;
+}
+
+// the register-direct instance (natural-order C2C external): shape from kernels::RegDirect
+template <int E, int DIR, int TW>
+KernelEntry make_entry_reg()
+{
+    using Rd = kernels::RegDirect<E>;
+    KernelEntry k = make_entry_shape<E, Rd::B, Rd::TILE_E, 1, Rd::MINB, kernels::MODE_C2C, DIR, 1, kernels::IO_REG, TW, 1, -1>();
+    k.ctas = -1;              // one CTA per tile (non-persistent grid)
+    k.prefer = Rd::PREFER;    // 1 = used by default for this size; the TMA instance stays reachable with io = 2
     return k;
 }
 
@@ -60,7 +72,7 @@ template <int E>
 EntryList build_entries()
 {
     using namespace kernels;
-    static KernelEntry tab[96];
+    static KernelEntry tab[104];
     static int n = 0;
     if (n == 0) {
         int i = 0;
@@ -82,6 +94,12 @@ EntryList build_entries()
             SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_MUFU, 1);
             SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_MUFU, 1);
             SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_MUFU, 1);
+        }
+        // register-direct input (IO_REG): 1024-point natural-order C2C -- R = 32, one warp per transform, two transforms per
+        // 64-thread CTA, one CTA per tile, launched with the driver's default L1 carve-out (tuning.hpp, RegDirect)
+        if constexpr (RegDirect<E>::ON) {
+            tab[i++] = make_entry_reg<E, 0, TW_LUT>(); tab[i++] = make_entry_reg<E, 1, TW_LUT>();
+            tab[i++] = make_entry_reg<E, 0, TW_MUFU>(); tab[i++] = make_entry_reg<E, 1, TW_MUFU>();
         }
         // C2C multiple (FFT_multiple_benchmark, 100 reps in place): compute-bound, LDG staging only
         SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_LUT, 100);

@@ -175,6 +175,28 @@ struct TuningC2R12 {
     static constexpr int B = 5, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
+// Register-direct input (IO_REG) for natural-order C2C: global -> registers -> passes -> global, shared memory only for the
+// exchange.  With the driver's DEFAULT L1 carve-out (not max shared) the LDG/STG path is as fast as cuFFT's kernels
+// (tools/fftlike_copy.cu): 1.252 ms at 1024 points against 1.29-1.30 ms for the TMA path
+// (profiles/r01_tune_register_direct_carveout_default.csv).  PREFER follows the sustained bench step, and there the
+// 12-warps-per-SM shape loses: 1.263 vs 1.304 ms in single launches but 1.42 vs 1.34 ms inside the power-capped step
+// (profiles/r01_register_direct_1024_burst_vs_sustained.json).  The instance stays reachable with io = 4.
+template <int E>
+struct RegDirect {
+    static constexpr bool ON = false, PREFER = false;
+    static constexpr int B = 4, TILE_E = 10, MINB = 8;
+};
+template <>
+struct RegDirect<10> {
+    static constexpr bool ON = true;
+#if defined(SMFFT_REGDIRECT_DEFAULT)
+    static constexpr bool PREFER = true;
+#else
+    static constexpr bool PREFER = false;
+#endif
+    static constexpr int B = 5, TILE_E = 11, MINB = 6;
+};
+
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
 // (compute-bound: R = 32 pays at 512 and 1024 points, C2C 0.88 / 1.09 ms vs 1.12 / 1.13 ms, R2C 1.21 / 1.23 vs
 // 1.28 / 1.27 ms, not at 4096)

@@ -52,7 +52,7 @@ def run_c2c(sm, x, inverse, reorder):
     return c64(dy)
 
 
-@pytest.mark.parametrize("io", [0, 1, 2, 3])   # auto / thread-staged / TMA in+out / TMA in, registers out
+@pytest.mark.parametrize("io", [0, 1, 2, 3, 4])   # auto / thread-staged / TMA in+out / TMA in, registers out / register-direct (1024 natural, else default)
 @pytest.mark.parametrize("tw", [0, 1])
 @pytest.mark.parametrize("n", SIZES)
 def test_c2c_vs_oracle(sm, n, io, tw):
