@@ -146,6 +146,17 @@ using namespace smfft;
 
 #include "emu_run_cfg.hpp"
 
+// what the product would run for (e, mode): arith flags | B << 4 | mirrored R2C << 8 | mirrored C2R << 9 | threads << 12
+template <int E, int MODE>
+static int product_flavour()
+{
+    using Tn = typename kernels::ShapeFor<E, MODE, 1, 1>::type;
+    constexpr int ARITH = kernels::ArithFor<E, MODE, 1, 1>::value;
+    using XL = typename std::conditional<Tn::B == 5, detail::LayoutSW256, detail::LayoutSW128>::type;
+    using C = detail::BlockCfg<E, Tn::B, Tn::F, MODE == 2, 1, TW_LUT, detail::LayoutSW128, XL, true, true, ARITH>;
+    return ARITH | (Tn::B << 4) | ((MODE == 1 && detail::MirrorR2C<C>::OK) << 8) | ((MODE == 2 && detail::MirrorC2R<C>::OK) << 9) | (C::THREADS << 12);
+}
+
 extern "C" {
 
 // product shapes (tuning.hpp): e = log2 complex length
@@ -168,6 +179,14 @@ int emu_run(const void* in, void* out, int e, long long n_ffts, int mode, int di
     }
     SHAPE(5) SHAPE(6) SHAPE(7) SHAPE(8) SHAPE(9) SHAPE(10) SHAPE(11) SHAPE(12)
 #undef SHAPE
+    return -1;
+}
+
+int emu_product_flavour(int e, int mode)
+{
+#define PF(E) if (e == E) return mode == 0 ? product_flavour<E, 0>() : mode == 1 ? product_flavour<E, 1>() : product_flavour<E, 2>();
+    PF(5) PF(6) PF(7) PF(8) PF(9) PF(10) PF(11) PF(12)
+#undef PF
     return -1;
 }
 

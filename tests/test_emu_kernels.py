@@ -308,3 +308,26 @@ def test_dual_lane_multiple_and_one_hot(emu, e, b):
     run_dual(emu, oh, out, e, b, 2, IO_TMA)
     for row, p in enumerate(ps):
         assert int(np.rint((-np.angle(out[row, 1]) * n / (2 * np.pi)))) % n == perm[p]
+
+
+def test_product_flavours(emu):
+    """Guards the tuning table: which product instances use the packed add/subtract, the reversed plan and the mirrored
+    ownership of the real passes (a silent change of B or of a plan would lose the mirror without failing any numerics)."""
+    emu.emu_product_flavour.argtypes = [ctypes.c_int, ctypes.c_int]
+
+    def f(e, mode):
+        v = emu.emu_product_flavour(e, mode)
+        assert v >= 0
+        return {"arith": v & 15, "B": (v >> 4) & 15, "mirror_r2c": (v >> 8) & 1, "mirror_c2r": (v >> 9) & 1, "threads": v >> 12}
+
+    # R2C: mirrored at 4096 reals (R = 16, [16,16,8]) and 8192 reals (R = 32, [32,32,4]), packed add/sub there and at 64 reals
+    assert [f(e, R2C)["mirror_r2c"] for e in range(5, 13)] == [0, 0, 0, 0, 0, 0, 1, 1]
+    assert f(11, R2C)["B"] == 4 and f(12, R2C)["B"] == 5
+    assert [f(e, R2C)["arith"] for e in range(5, 13)] == [2, 0, 0, 0, 0, 0, 2, 2]
+    # C2R: packed add/sub everywhere; reversed plan + mirror at 4096 ([8,16,16]) and 8192 reals ([4,32,32])
+    assert [f(e, C2R)["arith"] for e in range(5, 13)] == [2, 2, 2, 2, 2, 2, 6, 6]
+    assert [f(e, C2R)["mirror_c2r"] for e in range(5, 13)] == [0, 0, 0, 0, 0, 0, 1, 1]
+    assert f(11, C2R)["B"] == 4 and f(12, C2R)["B"] == 5
+    # C2C natural order: R = 32 single-exchange plans at 512 / 1024 points, packed R = 16 at 2048 / 4096 points
+    assert [f(e, C2C)["B"] for e in range(5, 13)] == [4, 4, 4, 4, 5, 5, 4, 4]
+    assert [f(e, C2C)["arith"] for e in range(5, 13)] == [0, 0, 0, 0, 0, 0, 2, 2]
