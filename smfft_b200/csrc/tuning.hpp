@@ -179,7 +179,7 @@ struct TuningC2R12 {
 // exchange.  With the driver's DEFAULT L1 carve-out (not max shared) the LDG/STG path is as fast as cuFFT's kernels
 // (tools/fftlike_copy.cu): 1.252 ms at 1024 points against 1.29-1.30 ms for the TMA path
 // (profiles/r01_tune_register_direct_carveout_default.csv).  PREFER follows the sustained bench step, and there the
-// 12-warps-per-SM shape loses: 1.263 vs 1.304 ms in single launches but 1.42 vs 1.34 ms inside the power-capped step
+// shape loses even with 16 warps per SM: 1.257 vs 1.303 ms in single launches but 1.40 vs 1.34 ms inside the power-capped step
 // (profiles/r01_register_direct_1024_burst_vs_sustained.json).  The instance stays reachable with io = 4.
 template <int E>
 struct RegDirect {
@@ -194,7 +194,7 @@ struct RegDirect<10> {
 #else
     static constexpr bool PREFER = false;
 #endif
-    static constexpr int B = 5, TILE_E = 11, MINB = 6;
+    static constexpr int B = 5, TILE_E = 11, MINB = 8;  // 93 registers: eight CTAs = 16 warps per SM (six: 1.263 / 1.42 ms)
 };
 
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple
