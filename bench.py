@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 SIZES = [32, 64, 128, 256, 512, 1024, 2048, 4096]
 BATCH_POINTS = 1 << 29          # 4 GiB of float2
 BYTES_PER_POINT = 16            # 8 read + 8 written
-METRIC = "Batched FFT HBM GB/s & ms per 4 GB batch, N=32-4096, at 1/2/4/8 B200"
+METRIC = "Batched FFT HBM GB/s & ms per 4 GB batch, N=32\u20134096, at 1/2/4/8 B200"  # BASELINE.json metric, verbatim
 
 
 def configs():
@@ -178,10 +178,36 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # reported GPU baselines (outside the timed region, rank 0): recompiled reference kernels, cuFFT
 # ----------------------------------------------------------------------------------------------
-def reference_gpu_baseline(x, y, reps=3):
-    import ctypes
-
+def sustained_arm(launchers, steps, warmup=2):
+    """The protocol of the timed region, for any arm: `steps` back-to-back passes over the whole launcher list (the
+    16-launch step), every launch between two CUDA events on the launching stream; per key the median / min over the
+    steps.  launchers: [(key, callable)]; a key may repeat inside a step (cuFFT has no no-reorder mode)."""
     import torch
+
+    for _ in range(warmup):
+        for _, fn in launchers:
+            fn()
+    torch.cuda.synchronize()
+    rec = {}
+    for _ in range(steps):
+        for key, fn in launchers:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            rec.setdefault(key, []).append((e0, e1))
+    torch.cuda.synchronize()
+    out = {}
+    for key, evs in rec.items():
+        ts = [a.elapsed_time(b) for a, b in evs]
+        out[key] = {"ms": round(statistics.median(ts), 4), "ms_min": round(min(ts), 4)}
+    return out
+
+
+def reference_gpu_baseline(x, y, steps=5):
+    """the reference's own kernels rebuilt for sm_100a (oracle/_ref), through ITS FFT_external_benchmark (CT:583), in the
+    same sustained 16-launch step as the product"""
+    import ctypes
 
     so = os.path.join(ROOT, "oracle", "_ref", "libsmfft_ref_ct.so")
     if not os.path.exists(so):
@@ -191,26 +217,21 @@ def reference_gpu_baseline(x, y, reps=3):
         fn = getattr(ref, "_Z22FFT_external_benchmarkP6float2S0_iibbPd")
         fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_bool, ctypes.c_bool,
                        ctypes.POINTER(ctypes.c_double)]
-        out = {}
-        for n, reorder in configs():
-            best = None
-            for _ in range(reps + 1):
-                ms = ctypes.c_double(0)
-                fn(x.data_ptr(), y.data_ptr(), n, BATCH_POINTS // n, False, bool(reorder), ctypes.byref(ms))
-                torch.cuda.synchronize()
-                best = ms.value if best is None else min(best, ms.value)
-            out[f"{n}{'r' if reorder else 'n'}"] = round(best, 4)
+        ms = ctypes.c_double(0)
+        xp, yp = x.data_ptr(), y.data_ptr()
+        launchers = [(f"{n}{'r' if reorder else 'n'}", (lambda n=n, reorder=reorder: fn(xp, yp, n, BATCH_POINTS // n, False, bool(reorder), ctypes.byref(ms))))
+                     for n, reorder in configs()]
+        out = sustained_arm(launchers, steps)
+        out["how"] = "unmodified reference kernels (sm_100a rebuild), sustained 16-launch step, CUDA events per launch, median over %d steps" % steps
         return out
     except Exception as ex:  # pragma: no cover
         return {"error": str(ex)[:200]}
 
 
-def cufft_baseline(x, y, reps=5):
-    """cuFFT on the same buffers, as SURVEY.md 8d asks: plan created outside the timer, out of place, one cufftExecC2C
-    per timed launch (cuFFT called directly; torch.fft.fft(out=) goes through a temporary and an extra copy)."""
+def cufft_baseline(x, y, steps=5):
+    """cuFFT on the same buffers: plans created outside the timer, out of place, one cufftExecC2C per timed
+    launch, in the same sustained 16-launch step as the product (cuFFT has no no-reorder mode: each size runs twice per step)."""
     import ctypes
-
-    import torch
 
     lib = None
     for name in ("libcufft.so.11", "libcufft.so.12", "libcufft.so"):
@@ -221,30 +242,22 @@ def cufft_baseline(x, y, reps=5):
             continue
     if lib is None:
         return {"error": "libcufft not loadable"}
+    plans = {}
     try:
-        out = {"how": "cufftPlan1d(C2C, batch) + cufftExecC2C, out of place, plan outside the timer; min of %d" % reps}
         for n in SIZES:
             h = ctypes.c_int(0)
-            if lib.cufftPlan1d(ctypes.byref(h), n, 0x29, BATCH_POINTS // n) != 0:
-                out[str(n)] = None
-                continue
-            run = lambda: lib.cufftExecC2C(h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), -1)
-            run()
-            torch.cuda.synchronize()
-            best = None
-            for _ in range(reps):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                run()
-                e1.record()
-                torch.cuda.synchronize()
-                t = e0.elapsed_time(e1)
-                best = t if best is None else min(best, t)
-            out[str(n)] = round(best, 4)
-            lib.cufftDestroy(h)
+            if lib.cufftPlan1d(ctypes.byref(h), n, 0x29, BATCH_POINTS // n) == 0:
+                plans[n] = h
+        xp, yp = ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr())
+        launchers = [(str(n), (lambda n=n: lib.cufftExecC2C(plans[n], xp, yp, -1))) for n in SIZES if n in plans for _ in (0, 1)]
+        out = sustained_arm(launchers, steps)
+        out["how"] = "cufftPlan1d(C2C, batch) + cufftExecC2C, out of place, sustained 16-launch step (each size twice), CUDA events per launch, median over %d steps" % steps
         return out
     except Exception as ex:  # pragma: no cover
         return {"error": str(ex)[:200]}
+    finally:
+        for h in plans.values():
+            lib.cufftDestroy(h)
 
 
 def other_modes(x, y, reps=5):

@@ -20,7 +20,13 @@
  *     (checkCudaErrors -> exit(1), utils_cuda.h:12-22) the library never terminates the process;
  *   - counts are 64-bit (the reference's int indexing stops at 4 GiB);
  *   - work is launched on the CUDA stream given to smfft_set_stream (default: legacy stream 0,
- *     as the reference), on the current device.
+ *     as the reference) or passed to the *_stream entry points, on the current device.
+ * Thread safety (the reference is single-threaded, one global device, CT:15): every entry point may be
+ * called concurrently from several host threads, on one device or on several ("one host thread per
+ * GPU").  The stream of smfft_set_stream, smfft_last_error() and smfft_last_error_code() are PER
+ * THREAD; options (smfft_set_option) are process-wide; per-device state (twiddle table, kernel
+ * attributes, pipeline buffers) is created on first use under a per-device lock;
+ * smfft_pipeline_host calls on one device serialise.
  * There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
  */
 #ifndef SMFFT_H
@@ -30,7 +36,14 @@
 extern "C" {
 #endif
 
-#define SMFFT_VERSION 100
+#define SMFFT_VERSION 200
+
+/* smfft_last_error_code(): what kind of failure the last non-zero return on this thread was.  The reference
+ * tells them apart too: a wrong FFT length only prints (CT:656-658), a CUDA failure exits (utils_cuda.h:12-22). */
+#define SMFFT_OK 0
+#define SMFFT_ERR_ARGUMENT 1 /* wrong FFT length, bad count, misaligned pointer, unknown option */
+#define SMFFT_ERR_CUDA 2     /* a CUDA runtime / driver call or the kernel itself failed */
+#define SMFFT_ERR_MEMORY 3   /* not enough device memory (CT:839-847) */
 
 /* replaces FFT_init() (CT:576-581, ST:299-303, RC:388-392): builds the twiddle table, opts the
  * kernels into >48 KB dynamic shared memory.  Idempotent; called lazily by everything else. */
@@ -49,8 +62,11 @@ int smfft_external_benchmark(const void* d_in, void* d_out, int fft_size, long l
  * overflow by design).  n_ffts < 100: *ms = -1, returns 1 (CT:670-673). */
 int smfft_multiple_benchmark(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder,
                              double* ms);
-/* untimed launch of the same transform (what a caller embeds in its own stream) */
+/* untimed launch of the same transform (what a caller embeds in its own stream): on the calling thread's
+ * smfft_set_stream stream, or on an explicit cudaStream_t (as void*; NULL = legacy default stream) */
 int smfft_exec_c2c(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder);
+int smfft_exec_c2c_stream(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder,
+                          void* stream);
 
 /* ---- Stockham C2C: N = 32..4096, natural order ------------------------------------------------
  * replaces void FFT_external_benchmark(float2*, float2*, int, int, double*)            ST:306-345
@@ -72,6 +88,15 @@ int smfft_r2c_c2r_external_benchmark(const void* d_in, void* d_out, int fft_size
                                      double* ms);
 int smfft_r2c_multiple_benchmark(const void* d_in, void* d_out, int fft_size, long long n_ffts, double* ms);
 int smfft_exec_r2c_c2r(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse);
+int smfft_exec_r2c_c2r_stream(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, void* stream);
+
+/* ---- the repeated path, untimed, with a repetition count that keeps the values finite -------------
+ * SMFFT_DIT_multiple / FFT_GPU_multiple / FFT_GPU_R2C_C2R_multiple (CT:553-572, ST:262-278, RC:367-384) apply the
+ * transform NREUSES = 100 times in place, so their outputs overflow and the reference never checks them.  This entry
+ * runs the same kernels with reps = 3 (or 100) over ALL n_ffts transforms of d_in, so tests can compare F^3 x with
+ * the oracle.  mode: 0 = C2C, 1 = R2C (forward). */
+int smfft_exec_repeated(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder, int mode,
+                        int reps);
 
 /* ---- host-pointer end-to-end drivers ------------------------------------------------------------
  * replaces int GPU_smFFT_4elements(float2* h_in, float2* h_out, int FFT_size, int nFFTs,
@@ -88,6 +113,9 @@ int smfft_r2c_c2r_host(const void* h_in, void* h_out, int fft_size, long long n_
  * buffers: the end-to-end path bench.py times as `e2e`.  mode: 0 = CT C2C, 1 = R2C, 2 = C2R. */
 int smfft_pipeline_host(const void* h_in, void* h_out, int fft_size, long long n_ffts, int inverse, int reorder,
                         int mode, long long chunk_ffts, double* ms);
+/* frees the current device's pipeline buffers (6 x chunk bytes), streams and events; they are re-created on the next
+ * smfft_pipeline_host call */
+int smfft_pipeline_release(void);
 
 /* ---- knobs -------------------------------------------------------------------------------------
  * keys: "io" (0 = measured best TMA staging per size [default], 1 = LDG/STG staging by the threads,
@@ -95,15 +123,16 @@ int smfft_pipeline_host(const void* h_in, void* h_out, int fft_size, long long n
  * exists [1024-point natural-order C2C], the default elsewhere), "twiddle" (0 = table+powers
  * [default], 1 = MUFU __sincosf), "quirk_4096" (1 = reproduce FFT_4096_inverse_noreorder running
  * the forward transform, CT/SM_FFT_parameters.cuh:388; default 0 = mathematically correct),
- * "ctas_per_sm" (0 = built-in), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
+ * "ctas_per_sm" (0 = built-in), "pipeline_chunk_mib" (default chunk of smfft_pipeline_host, 1..1024, default 128), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
  * of shared memory), "device_sms" (read-only). */
 int smfft_set_option(const char* key, int value);
 int smfft_get_option(const char* key);
-/* CUDA stream (cudaStream_t as void*) used for launches and event timing; NULL = legacy default */
+/* CUDA stream (cudaStream_t as void*) used by THIS host thread's launches and event timing; NULL = legacy default */
 int smfft_set_stream(void* stream);
 /* number of kernels launched by this library since load (bench.py's gpu_launches evidence) */
 long long smfft_launch_count(void);
 const char* smfft_last_error(void);
+int smfft_last_error_code(void);
 int smfft_version(void);
 
 #ifdef __cplusplus

@@ -16,6 +16,8 @@ from .api import (  # noqa: F401
     R2C_multiple_benchmark,
     exec_c2c,
     exec_r2c_c2r,
+    exec_repeated,
+    pipeline_release,
     c2c_host,
     pipeline_host,
     set_option,

@@ -2,6 +2,7 @@
 // See include/smfft_compat.hpp for the reference lines each function replaces.
 #include <cufft.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "smfft.h"
 #include "smfft_compat.hpp"
@@ -13,14 +14,26 @@ static void report(int rc, const char* what)
     if (rc) fprintf(stderr, "smfft (%s): %s\n", what, smfft_last_error());
 }
 
+// The reference tells two failures of a launcher apart: an unsupported FFT length only prints "Error wrong FFT length!"
+// and the launcher carries on (CT:656-658, ST:337-339, RC:425-427); anything CUDA goes through checkCudaErrors, which
+// prints the error and ends the process (utils_cuda.h:12-22).  Same here, from the C ABI's error code.
+static void launcher_failed(const char* what)
+{
+    if (smfft_last_error_code() == SMFFT_ERR_ARGUMENT) {
+        printf("Error wrong FFT length!\n");
+        return;
+    }
+    fprintf(stderr, "CUDA error in %s: %s\n", what, smfft_last_error());
+    exit(1);
+}
+
 VIS void FFT_init() { report(smfft_init(), "FFT_init"); }
 
 // ---- Cooley-Tukey ----
 VIS int FFT_external_benchmark(float2* d_input, float2* d_output, int FFT_size, int nFFTs, bool inverse, bool reorder, double* FFT_time)
 {
-    int rc = smfft_external_benchmark(d_input, d_output, FFT_size, nFFTs, inverse, reorder, FFT_time);
-    if (rc) printf("Error wrong FFT length!\n");  // CT:656-658 (the reference still returns 0 here)
-    return 0;
+    if (smfft_external_benchmark(d_input, d_output, FFT_size, nFFTs, inverse, reorder, FFT_time)) launcher_failed("FFT_external_benchmark");
+    return 0;  // CT:656-664: the reference returns 0 after the wrong-length message too
 }
 VIS int FFT_multiple_benchmark(float2* d_input, float2* d_output, int FFT_size, int nFFTs, bool inverse, bool reorder, double* FFT_time)
 {
@@ -28,7 +41,7 @@ VIS int FFT_multiple_benchmark(float2* d_input, float2* d_output, int FFT_size, 
         *FFT_time = -1;
         return 1;
     }
-    if (smfft_multiple_benchmark(d_input, d_output, FFT_size, nFFTs, inverse, reorder, FFT_time)) printf("Error wrong FFT length!\n");
+    if (smfft_multiple_benchmark(d_input, d_output, FFT_size, nFFTs, inverse, reorder, FFT_time)) launcher_failed("FFT_multiple_benchmark");
     return 0;
 }
 VIS int GPU_smFFT_4elements(float2* h_input, float2* h_output, int FFT_size, int nFFTs, bool inverse, bool reorder, int nRuns,
@@ -86,12 +99,12 @@ VIS int GPU_cuFFT(float2* h_input, float2* h_output, int FFT_size, int nFFTs, bo
 // ---- Stockham C2C ----
 VIS void FFT_external_benchmark(float2* d_input, float2* d_output, int FFT_size, int nFFTs, double* FFT_time)
 {
-    if (smfft_stockham_external_benchmark(d_input, d_output, FFT_size, nFFTs, 1, FFT_time)) printf("Error wrong FFT length!\n");
+    if (smfft_stockham_external_benchmark(d_input, d_output, FFT_size, nFFTs, 1, FFT_time)) launcher_failed("FFT_external_benchmark");
 }
 VIS void FFT_multiple_benchmark(float2* d_input, float2* d_output, int FFT_size, int nFFTs, double* FFT_time)
 {
     if (nFFTs / 100 == 0) return;
-    if (smfft_stockham_multiple_benchmark(d_input, d_output, FFT_size, nFFTs, 1, FFT_time)) printf("Error wrong FFT length!\n");
+    if (smfft_stockham_multiple_benchmark(d_input, d_output, FFT_size, nFFTs, 1, FFT_time)) launcher_failed("FFT_multiple_benchmark");
 }
 VIS int GPU_FFT_C2C_Stockham(float2* h_input, float2* h_output, int FFT_size, int nFFTs, int nRuns, double* single_ex_time,
                              double* multi_ex_time)
@@ -113,12 +126,12 @@ VIS int GPU_cuFFT(float2* h_input, float2* h_output, int FFT_size, int nFFTs, in
 // ---- Stockham R2C / C2R ----
 VIS void FFT_external_benchmark(float* d_input, float* d_output, int FFT_size, int nFFTs, int inverse, double* FFT_time)
 {
-    if (smfft_r2c_c2r_external_benchmark(d_input, d_output, FFT_size, nFFTs, inverse, FFT_time)) printf("Error wrong FFT length!\n");
+    if (smfft_r2c_c2r_external_benchmark(d_input, d_output, FFT_size, nFFTs, inverse, FFT_time)) launcher_failed("FFT_external_benchmark");
 }
 VIS void FFT_multiple_benchmark(float* d_input, float* d_output, int FFT_size, int nFFTs, double* FFT_time)
 {
     if (nFFTs / 100 == 0) return;
-    if (smfft_r2c_multiple_benchmark(d_input, d_output, FFT_size, nFFTs, FFT_time)) printf("Error wrong FFT length!\n");
+    if (smfft_r2c_multiple_benchmark(d_input, d_output, FFT_size, nFFTs, FFT_time)) launcher_failed("FFT_multiple_benchmark");
 }
 VIS int GPU_smFFT_R2C(float2* h_output, float* h_input, int FFT_size, int nFFTs, int nRuns)
 {

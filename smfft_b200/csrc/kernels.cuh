@@ -184,6 +184,10 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
                 };
                 tile_transform_to_global<C, MODE, REPS>(stage_ptr(k), stw, args.gout + p0, args.n_points - p0,
                                                         detail::hook_at<(PF < 0 ? 0 : PF)>(refill));
+                // this buffer was written through the generic proxy (exchanges, real-pass scratch) and is refilled by a
+                // TMA load (async proxy) behind the first barrier of the next tile: order the two, as the PTX memory
+                // model asks (the IO_TMA path fences before its store for the same reason)
+                plat::fence_proxy_async();
             }
         }
     } else if constexpr (IO == IO_REG) {

@@ -72,9 +72,15 @@ template <int E>
 EntryList build_entries()
 {
     using namespace kernels;
-    static KernelEntry tab[104];
-    static int n = 0;
-    if (n == 0) {
+    // filled exactly once, by whichever thread gets here first (C++11 guarantees the initialisation of a function-local
+    // static is thread-safe); read-only afterwards
+    struct Table {
+        KernelEntry tab[112];
+        int n = 0;
+    };
+    static const Table table = [] {
+        Table t;
+        KernelEntry* tab = t.tab;
         int i = 0;
 #define SMFFT_ADD(...) tab[i++] = make_entry<E, __VA_ARGS__>()
         // C2C external (FFT_external_benchmark): dir x reorder x io x twiddle
@@ -113,10 +119,16 @@ EntryList build_entries()
         SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_LDG, TW_MUFU, 1);
         // R2C multiple (forward only, as RC:445-457)
         SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_MUFU, 100);
+        // the same repeated path with THREE repetitions: F(F(F(x))) stays finite, so its values can be checked against the
+        // oracle on the GPU (smfft_exec_repeated; the 100-rep instances overflow by design)
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_LUT, 3); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_LUT, 3);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 3); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 3);
+        SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_LUT, 3);
 #undef SMFFT_ADD
-        n = i;
-    }
-    return EntryList{tab, n};
+        t.n = i;
+        return t;
+    }();
+    return EntryList{table.tab, table.n};
 }
 
 // defined one per translation unit (inst_e5.cu ... inst_e12.cu) so the sizes compile in parallel

@@ -79,6 +79,38 @@ extern "C" int compat_r2c_c2r_external(float* d_in, float* d_out, int n, int nff
     return (int)cudaGetLastError();
 }
 
+extern "C" int compat_stockham_multiple(float2* d_in, float2* d_out, int n, int nffts)
+{
+    const int grid = nffts / 100;  // ST:351
+    if (grid == 0) return -2;
+    switch (n) {
+        case 256: FFT_GPU_multiple<FFT_256><<<grid, n / 4, n * 8>>>(d_in, d_out); break;
+        case 512: FFT_GPU_multiple<FFT_512><<<grid, n / 4, n * 8>>>(d_in, d_out); break;
+        case 1024: FFT_GPU_multiple<FFT_1024><<<grid, n / 4, n * 8>>>(d_in, d_out); break;
+        case 2048: FFT_GPU_multiple<FFT_2048><<<grid, n / 4, n * 8>>>(d_in, d_out); break;
+        case 4096: FFT_GPU_multiple<FFT_4096><<<grid, n / 4, n * 8>>>(d_in, d_out); break;
+        default: return -1;
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int compat_r2c_multiple(float* d_in, float* d_out, int n, int nffts)
+{
+    float2* in = (float2*)d_in;
+    float2* out = (float2*)d_out;
+    const int grid = nffts / 100, block = (n >> 1) / 4;  // RC:438-439
+    if (grid == 0) return -2;
+    switch (n) {
+        case 256: FFT_GPU_R2C_C2R_multiple<FFT_128, FFT_forward><<<grid, block>>>(in, out); break;
+        case 512: FFT_GPU_R2C_C2R_multiple<FFT_256, FFT_forward><<<grid, block>>>(in, out); break;
+        case 1024: FFT_GPU_R2C_C2R_multiple<FFT_512, FFT_forward><<<grid, block>>>(in, out); break;
+        case 2048: FFT_GPU_R2C_C2R_multiple<FFT_1024, FFT_forward><<<grid, block>>>(in, out); break;
+        case 4096: FFT_GPU_R2C_C2R_multiple<FFT_2048, FFT_forward><<<grid, block>>>(in, out); break;
+        default: return -1;
+    }
+    return (int)cudaGetLastError();
+}
+
 // a user kernel that calls the device function directly: forward (no-reorder) -> pointwise filter
 // -> inverse in one launch, the convolution use case SMFFT exists for (README.md:2, 10-14).
 // Filter H is given in natural frequency order; with the no-reorder pair the data is transformed

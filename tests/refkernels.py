@@ -63,3 +63,12 @@ def rc_external(d_in, d_out, n, nffts, inverse) -> float:
     ms = ctypes.c_double(0)
     fn(d_in.data_ptr(), d_out.data_ptr(), n, nffts, int(inverse), ctypes.byref(ms))
     return ms.value
+
+
+def rc_multiple(d_in, d_out, n, nffts) -> float:
+    """void FFT_multiple_benchmark(float*, float*, int, int, double*)  RC/...:435 (forward only)"""
+    fn = getattr(_lib("rc"), "_Z22FFT_multiple_benchmarkPfS_iiPd")
+    fn.argtypes = [P, P, I, I, D]
+    ms = ctypes.c_double(0)
+    fn(d_in.data_ptr(), d_out.data_ptr(), n, nffts, ctypes.byref(ms))
+    return ms.value

@@ -28,7 +28,7 @@ def test_exports_every_declared_symbol(lib):
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/smfft.h but not exported"
-    assert lib.smfft_version() == 100
+    assert lib.smfft_version() == 200
 
 
 def test_exports_nothing_from_the_oracle(lib):

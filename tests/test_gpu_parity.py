@@ -402,3 +402,193 @@ def test_32GiB_batch_64bit_indexing(sm):
         assert O.rel_l2(ys, O.r2c_packed_fp64(xs)) < TOL
     del x, y
     torch.cuda.empty_cache()
+
+
+# ---- round 2: the holes the round-1 review named -----------------------------------------------------------------
+
+@pytest.mark.parametrize("n", SIZES)
+def test_repeated_path_values_c2c(sm, n):
+    """The FFT_multiple kernels (in-place repetitions with their inter-rep barrier, CT:553-572) with THREE repetitions:
+    F(F(F(x))) compared with the oracle applied three times -- for reorder, no-reorder, forward and inverse."""
+    nf = 2 * (8192 // n) + 3     # several tiles plus a ragged tail
+    x = (O.uniform_c64(nf, n, seed=n + 11) / np.float32(n)).astype(np.complex64)
+    dx = to_dev(x)
+    for inverse in (False, True):
+        for reorder in (True, False):
+            dy = torch.zeros_like(dx)
+            sm.exec_repeated(dx, dy, n, nf, inverse, reorder, 0, 3)
+            torch.cuda.synchronize()
+            want64, want32 = x.astype(np.complex128), x
+            for _ in range(3):
+                want64 = O.ct_c2c_fp64(want64, inverse, reorder)
+                want32 = O.c_ct_c2c(want32, inverse, reorder)       # the CPU restatement, fp32 like the kernels
+            assert O.rel_l2(c64(dy), want64) < TOL, (n, inverse, reorder)
+            assert O.rel_l2(c64(dy), want32) < TOL, (n, inverse, reorder)
+    with pytest.raises(sm.SmfftError):
+        sm.exec_repeated(dx, dy, n, nf, False, True, 0, 7)          # only the 3- and 100-rep instances exist
+
+
+@pytest.mark.parametrize("n", [64, 256, 512, 1024, 2048, 4096, 8192])
+def test_repeated_path_values_r2c(sm, n):
+    """FFT_GPU_R2C_C2R_multiple (RC:367-384) re-reads its packed spectrum as reals on every repetition; three of them."""
+    nf = 2 * (8192 // n) + 3
+    x = (O.uniform_f32(nf, n, seed=n + 13) / np.float32(n)).astype(np.float32)
+    dx = to_dev(x)
+    dy = torch.zeros_like(dx)
+    sm.exec_repeated(dx, dy, n, nf, False, True, 1, 3)
+    torch.cuda.synchronize()
+    want64, want32 = x.astype(np.float64), x
+    for _ in range(3):
+        want64 = np.ascontiguousarray(O.r2c_packed_fp64(want64)).view(np.float64).reshape(nf, n)
+        want32 = np.ascontiguousarray(O.c_r2c(want32)).view(np.float32).reshape(nf, n)
+    got = dy.cpu().numpy()
+    assert O.rel_l2(got, want64) < TOL
+    assert O.rel_l2(got, want32) < TOL
+
+
+def test_full_size_properties_4GiB_stockham_and_real(sm):
+    """BASELINE.json configs[2] and configs[3] at their full sizes: Stockham inverse on 2^29 points and R2C / C2R on 2^30
+    reals (4 GiB), the sizes the bench times.  Sampled rows (first / middle / last transforms of the batch: the persistent
+    grid's tail logic) against the oracle and FP64, and the round trips  forward(inverse(x)) = N x,  C2R(R2C(x)) = N/2 x."""
+    pts = 1 << 29
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(20260102)
+    x = torch.rand((pts, 2), device="cuda", generator=gen)
+    y = torch.empty_like(x)
+    z = torch.empty_like(x)
+    for n in (256, 2048, 4096):                                   # Stockham C2C, inverse (the reference's direction, ST:70-78)
+        nf = pts // n
+        ms = sm.Stockham_external_benchmark(x, y, n, nf, True)
+        assert ms > 0
+        sm.Stockham_external_benchmark(y, z, n, nf, False)
+        torch.cuda.synchronize()
+        z.div_(n)
+        err = (torch.linalg.vector_norm((z - x).double()) / torch.linalg.vector_norm(x.double())).item()
+        assert err < TOL, (n, err)
+        for row0 in (0, nf // 2 - 3, nf - 8):
+            xs = c64(x.view(nf, n, 2)[row0:row0 + 8])
+            ys = c64(y.view(nf, n, 2)[row0:row0 + 8])
+            assert O.rel_l2(ys, O.stockham_c2c_fp64(xs, True)) < TOL, (n, row0)
+            assert O.rel_l2(ys, O.c_ct_c2c(xs, True, True)) < TOL, (n, row0)
+    xr = x.view(-1)                                                # 2^30 reals
+    zr = z.view(-1)
+    for n in (512, 2048, 4096, 8192):                              # real transform lengths; 4096 is the reference's largest
+        nf = 2 * pts // n
+        sm.exec_r2c_c2r(xr, y, n, nf, 0)
+        sm.exec_r2c_c2r(y, zr, n, nf, 1)
+        torch.cuda.synchronize()
+        zr.div_(n / 2)
+        err = (torch.linalg.vector_norm((zr - xr).double()) / torch.linalg.vector_norm(xr.double())).item()
+        assert err < TOL, (n, err)
+        for row0 in (0, nf // 2 - 3, nf - 8):
+            xs = xr.view(nf, n)[row0:row0 + 8].cpu().numpy()
+            ys = c64(y.view(nf, n // 2, 2)[row0:row0 + 8])
+            assert O.rel_l2(ys, O.c_r2c(xs)) < TOL, (n, row0)
+            assert O.rel_l2(ys, O.r2c_packed_fp64(xs)) < TOL, (n, row0)
+        # C2R of an arbitrary packed spectrum at full size (not only of an R2C result): sampled rows vs FP64
+        sm.exec_r2c_c2r(x, zr, n, nf, 1)
+        torch.cuda.synchronize()
+        for row0 in (0, nf - 8):
+            hs = c64(x.view(nf, n // 2, 2)[row0:row0 + 8])
+            assert O.rel_l2(zr.view(nf, n)[row0:row0 + 8].cpu().numpy(), O.c2r_packed_fp64(hs)) < TOL, (n, row0)
+    del x, y, z
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n", [64, 128, 512, 2048])
+@pytest.mark.parametrize("io", [0, 1, 2, 3])
+def test_in_place_every_staging(sm, n, io):
+    """d_output == d_input for the sizes and stagings the first in-place test left out: N = 128 (whose default stores
+    from registers, IO_TMA_STG) and every staging explicitly.  Safe because a tile is completely staged (TMA load or
+    thread copy) before any of its results is written, and tiles do not overlap."""
+    sm.set_option("io", io)
+    nf = 3 * (8192 // n) + 1
+    x = O.uniform_c64(nf, n, seed=n + 17)
+    for inverse, reorder in ((False, True), (True, False)):
+        d = to_dev(x)
+        sm.exec_c2c(d, d, n, nf, inverse, reorder)
+        torch.cuda.synchronize()
+        assert O.rel_l2(c64(d), O.ct_c2c_fp64(x, inverse, reorder)) < TOL, (n, io, inverse, reorder)
+    sm.set_option("io", 0)
+
+
+@pytest.mark.parametrize("n", [64, 256, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("io", [0, 1, 2, 3])
+def test_in_place_r2c_c2r(sm, n, io):
+    """R2C and C2R in place: input and output of one transform occupy the same bytes (N reals <-> N/2 packed bins)."""
+    sm.set_option("io", io)
+    nf = 2 * (8192 // n) + 3
+    x = O.uniform_f32(nf, n, seed=n + 19)
+    d = to_dev(x)
+    sm.exec_r2c_c2r(d, d, n, nf, 0)
+    torch.cuda.synchronize()
+    got = d.cpu().numpy().view(np.complex64).reshape(nf, n // 2)
+    assert O.rel_l2(got, O.r2c_packed_fp64(x)) < TOL, (n, io)
+    sm.exec_r2c_c2r(d, d, n, nf, 1)
+    torch.cuda.synchronize()
+    assert O.rel_l2(d.cpu().numpy() / (n / 2), x) < TOL, (n, io)
+    sm.set_option("io", 0)
+
+
+def test_host_threads_concurrently(sm):
+    """The C ABI from several host threads at once (one thread per GPU where the box has more than one, else all on
+    cuda:0, each on its own stream): per-thread streams and error text, per-device state behind its own lock, the
+    pipeline context owned by the device (launch.cu).  Every thread checks its own results against FP64."""
+    import threading
+
+    ndev = torch.cuda.device_count()
+    nthreads = 4
+    errors = []
+
+    def work(tid):
+        try:
+            dev = tid % ndev
+            torch.cuda.set_device(dev)
+            stream = torch.cuda.Stream(device=dev)
+            for it in range(6):
+                n = [32, 256, 1024, 4096][(tid + it) % 4]
+                nf = 3 * (8192 // n) + tid + 1
+                x = O.uniform_c64(nf, n, seed=100 * tid + it)
+                with torch.cuda.stream(stream):
+                    dx = to_dev(x).to(f"cuda:{dev}")
+                    dy = torch.zeros_like(dx)
+                    sm.exec_c2c(dx, dy, n, nf, bool(it & 1), bool(tid & 1))
+                    ms = sm.FFT_external_benchmark(dx, dy, n, nf, bool(it & 1), bool(tid & 1))
+                stream.synchronize()
+                assert ms > 0
+                err = O.rel_l2(c64(dy), O.ct_c2c_fp64(x, bool(it & 1), bool(tid & 1)))
+                assert err < TOL, (tid, it, n, err)
+                # a failing call on this thread must not disturb the others' error state or results
+                with pytest.raises(sm.SmfftError, match="wrong FFT length"):
+                    sm.exec_c2c(dx, dy, 48, 1, False, True)
+                # the host pipeline: its context belongs to the device, concurrent calls on one device serialise
+                hx = torch.from_numpy(x.view(np.float32).reshape(nf, n, 2)).pin_memory()
+                hy = torch.zeros_like(hx).pin_memory()
+                assert sm.pipeline_host(hx, hy, n, nf, False, True, 0, 7) > 0
+                assert O.rel_l2(c64(hy), O.ct_c2c_fp64(x, False, True)) < TOL
+        except BaseException as ex:  # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    torch.cuda.set_device(0)
+    assert not errors, errors
+    sm.pipeline_release()
+    sm.pipeline_release()   # idempotent
+
+
+def test_python_wrappers_check_their_buffers(sm):
+    """api.py refuses tensors that do not cover nFFTs * FFT_size elements, are not contiguous or live on the wrong side."""
+    x = torch.zeros((100, 1024, 2), device="cuda")
+    y = torch.zeros_like(x)
+    with pytest.raises(sm.SmfftError, match="needs"):
+        sm.exec_c2c(x, y, 1024, 101, False, True)
+    with pytest.raises(sm.SmfftError, match="contiguous"):
+        sm.exec_c2c(x.transpose(0, 1), y, 1024, 100, False, True)
+    with pytest.raises(sm.SmfftError, match="CUDA"):
+        sm.exec_c2c(x.cpu(), y, 1024, 100, False, True)
+    with pytest.raises(sm.SmfftError, match="fft|FFT"):
+        sm.pipeline_host(x.cpu(), y.cpu(), 0, 10)                  # validated before it is used as a divisor
