@@ -127,6 +127,9 @@ int smfft_pipeline_release(void);
  * of shared memory), "device_sms" (read-only). */
 int smfft_set_option(const char* key, int value);
 int smfft_get_option(const char* key);
+/* device address of the current device's twiddle table W_8192^j = exp(-2 pi i j / 8192), j = 0..8191 (float2, rounded
+ * from FP64): what smfft::BlockFFT<..., TW_LUT>::fill_twiddles (include/smfft/device.cuh) reads.  NULL on failure. */
+const void* smfft_twiddle_table(void);
 /* CUDA stream (cudaStream_t as void*) used by THIS host thread's launches and event timing; NULL = legacy default */
 int smfft_set_stream(void* stream);
 /* number of kernels launched by this library since load (bench.py's gpu_launches evidence) */

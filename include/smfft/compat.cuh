@@ -20,15 +20,17 @@
 //     implementation uses exactly fft_length of them (XOR-swizzled exchanges need no padding);
 //   * the caller synchronises before the call; do_SMFFT_CT_DIT does not synchronise on exit
 //     (the caller does, CT:543-546), the Stockham functions end with __syncthreads() (ST:239).
-// Internally: radix-4 register passes (4 points per thread IS the reference's contract), exchanges
-// in a bank-conflict-free swizzled layout inside the same buffer, MUFU twiddles like the reference
-// (no table pointer exists in this API), bit reversal folded into the first read.
+// Internally (detail/compat_core.cuh): radix-4 register stages (4 points per thread IS the reference's contract).
+// Tiles held by one warp (N <= 128) and every fft_reorder = 0 transform exchange through WARP SHUFFLES (detail/warp_fft.cuh:
+// one 4x4 register/lane transposition per radix-4 stage, shared memory only across warps, the bit reversal folded into the
+// addressing of the one store); natural-order transforms above 128 points run Stockham passes with exchanges in a
+// bank-conflict-free swizzled layout inside the same buffer.  MUFU twiddles like the reference (no table pointer exists in this API).
 //
 // FFT_4096_inverse_noreorder::fft_direction is 1 here (mathematically correct).  Define
 // SMFFT_COMPAT_QUIRK_4096 before including this header to reproduce the reference's 0
 // (SM_FFT_parameters.cuh:388), which makes that instance run the forward transform.
 #pragma once
-#include "detail/block_fft.cuh"
+#include "detail/compat_core.cuh"
 
 // ---- Cooley-Tukey trait classes (member names and values as in SM_FFT_parameters.cuh) -------------
 class FFT_Params {
@@ -113,25 +115,13 @@ public:
     static const int fft_direction = 1;
 };
 
-namespace smfft {
-namespace compat {
-
-// the native block FFT under the reference's thread contract: R = 4 points per thread, linear
-// tile on entry/exit, swizzled exchanges, 8-byte shared accesses only (no alignment demand)
-template <int EXP, int FFTS_PER_TILE, int DIR, int REORDER>
-using Cfg = detail::BlockCfg<EXP, 2, FFTS_PER_TILE, DIR, REORDER, TW_MUFU, detail::LayoutLinear, detail::LayoutSW128, false>;
-
-}  // namespace compat
-}  // namespace smfft
-
 // ---- device functions ------------------------------------------------------------------------------
 
 template <class const_params>
 __device__ __forceinline__ void do_SMFFT_CT_DIT(float2* s_input)
 {
-    using C = smfft::compat::Cfg<const_params::fft_exp, (const_params::fft_length >> const_params::fft_exp),
-                                 const_params::fft_direction, const_params::fft_reorder>;
-    smfft::detail::block_fft_tile<C, smfft::detail::XF_C2C>(s_input, nullptr);
+    smfft::compat::ct_dit<const_params::fft_exp, (const_params::fft_length >> const_params::fft_exp), const_params::fft_direction,
+                          const_params::fft_reorder>(s_input);
 }
 
 template <class const_params, class const_direction>
@@ -198,17 +188,15 @@ template <class const_params>
 __global__ void __launch_bounds__(const_params::fft_length / 4) SMFFT_DIT_external(float2* d_input, float2* d_output)
 {
     __shared__ float2 s_input[const_params::fft_sm_required];
-    smfft::compat::tile_in<const_params::fft_length>(s_input, d_input);
-    __syncthreads();
-    do_SMFFT_CT_DIT<const_params>(s_input);
-    __syncthreads();
-    smfft::compat::tile_out<const_params::fft_length>(s_input, d_output);
+    const size_t base = (size_t)blockIdx.x * const_params::fft_length;  // 64-bit: the reference's 32-bit index stops at 4 GiB
+    smfft::compat::ct_dit_external<const_params::fft_exp, (const_params::fft_length >> const_params::fft_exp), const_params::fft_direction,
+                                   const_params::fft_reorder>(s_input, d_input + base, d_output + base);
 }
 
 template <class const_params>
 __global__ void __launch_bounds__(const_params::fft_length / 4) SMFFT_DIT_multiple(float2* d_input, float2* d_output)
 {
-    __shared__ float2 s_input[const_params::fft_sm_required];
+    __shared__ __align__(16) float2 s_input[const_params::fft_sm_required];
     smfft::compat::tile_in<const_params::fft_length>(s_input, d_input);
     __syncthreads();
     for (int f = 0; f < SMFFT_NREUSES; f++) {

@@ -1,0 +1,66 @@
+// smfft/detail/compat_core.cuh -- which engine runs behind the reference-contract device functions.
+//
+// The contract (README.md:10-20 of the reference): the tile `s` is shared memory in natural, linear
+// order, in place; blockDim.x == tile points / 4; the caller synchronises before and after.  Three engines:
+//   * tiles held by ONE warp (32, 64, 128 points; four, two, one transform per 128-point tile): wf::warp_tile_fft --
+//     registers and warp shuffles only between the one read and the one write of the tile, no block barrier;
+//   * fft_reorder = 0 above 128 points: wf::block_fft_noreorder -- a 128-point warp-shuffle phase per warp, ONE exchange
+//     through the tile, a second warp-shuffle phase for the remaining bits;
+//   * natural order above 128 points: the Stockham radix-4 register passes of block_fft.cuh with swizzled exchanges.
+// Platform-neutral (platform.cuh), so tests/emu runs exactly this dispatch on the CPU.
+#pragma once
+#include "block_fft.cuh"
+#include "warp_fft.cuh"
+
+namespace smfft {
+namespace compat {
+
+// the native block FFT under the reference's thread contract: R = 4 points per thread, linear
+// tile on entry/exit, swizzled exchanges, 8-byte shared accesses only (no alignment demand)
+template <int EXP, int FFTS_PER_TILE, int DIR, int REORDER>
+using Cfg = detail::BlockCfg<EXP, 2, FFTS_PER_TILE, DIR, REORDER, TW_MUFU, detail::LayoutLinear, detail::LayoutSW128, false>;
+
+#ifndef SMFFT_COMPAT_ENGINE
+#define SMFFT_COMPAT_ENGINE 1  // 0: the shared-memory Stockham passes everywhere (the round-1 path, kept for A/B)
+#endif
+
+template <int EXP, int FFTS_PER_TILE, int DIR, int REORDER>
+SMFFT_DEV void ct_dit(float2* s)
+{
+    static_assert(EXP >= 5 && EXP <= 12 && (FFTS_PER_TILE << EXP) == (EXP < 7 ? 128 : (1 << EXP)), "tile = max(128, N) points");
+    if constexpr (SMFFT_COMPAT_ENGINE && EXP <= 7)
+        detail::wf::warp_tile_fft<EXP, DIR, REORDER>(s);
+    else if constexpr (SMFFT_COMPAT_ENGINE && !REORDER)
+        detail::wf::block_fft_noreorder<EXP, DIR>(s);
+    else
+        detail::block_fft_tile<Cfg<EXP, FFTS_PER_TILE, DIR, REORDER>, detail::XF_C2C>(s, nullptr);
+}
+
+// The body of the external wrapper kernels (SMFFT_DIT_external<P>, CT:534-551): the tile at gin -> transform -> gout, with
+// `s` (>= tile points) as scratch.  Same launch contract; the staging copies of the reference (4 LDG.64 -> 4 STS, barrier,
+// ..., barrier, 4 LDS -> 4 STG.64) are folded into the transform's own first read and last write.
+template <int EXP, int FFTS_PER_TILE, int DIR, int REORDER>
+SMFFT_DEV void ct_dit_external(float2* s, const float2* __restrict__ gin, float2* __restrict__ gout)
+{
+    if constexpr (SMFFT_COMPAT_ENGINE && EXP <= 7) {
+        detail::wf::warp_tile_fft_global<EXP, DIR, REORDER>(gin, gout);
+    } else if constexpr (SMFFT_COMPAT_ENGINE && !REORDER) {
+        detail::wf::block_fft_noreorder_global<EXP, DIR>(s, gin, gout);
+    } else if constexpr (SMFFT_COMPAT_ENGINE) {
+        using C = Cfg<EXP, FFTS_PER_TILE, DIR, REORDER>;
+        float2 v[C::R];
+        detail::load_global_natural<C>(v, gin, C::L);
+        detail::block_fft_preloaded_to_global<C, detail::XF_C2C>(v, s, nullptr, gout, C::L);
+    } else {
+        constexpr int L = FFTS_PER_TILE << EXP;
+        const int t = plat::tid();
+        detail::static_for<4>([&](auto Q) { plat::sts64(s + t + decltype(Q)::value * (L / 4), plat::ldg64_stream(gin + t + decltype(Q)::value * (L / 4))); });
+        plat::sync_block();
+        ct_dit<EXP, FFTS_PER_TILE, DIR, REORDER>(s);
+        plat::sync_block();
+        detail::static_for<4>([&](auto Q) { plat::stg64_stream(gout + t + decltype(Q)::value * (L / 4), plat::lds64(s + t + decltype(Q)::value * (L / 4))); });
+    }
+}
+
+}  // namespace compat
+}  // namespace smfft

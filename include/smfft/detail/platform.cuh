@@ -26,6 +26,10 @@ SMFFT_DEV int tid() { return (int)threadIdx.x; }
 SMFFT_DEV int bid() { return (int)blockIdx.x; }
 SMFFT_DEV int nblocks() { return (int)gridDim.x; }
 SMFFT_DEV void sync_block() { __syncthreads(); }
+SMFFT_DEV void sync_warp() { __syncwarp(); }
+SMFFT_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// warp exchange, all 32 lanes (the reference's shfl / shfl_xor helpers, CT/FFT-GPU-32bit.cu:30-44)
+SMFFT_DEV float shfl_xor(float v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 
 // shared-memory accessors: plain dereferences (the compiler proves the shared address space after
 // inlining and emits LDS/STS.64 and .128); kept as functions so the emulator can count bank conflicts.

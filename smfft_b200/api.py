@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
         L.smfft_launch_count.restype = LL
         L.smfft_last_error.argtypes = []
         L.smfft_last_error.restype = ctypes.c_char_p
+        L.smfft_twiddle_table.argtypes = []
+        L.smfft_twiddle_table.restype = ctypes.c_void_p
         _LIB = L
     return _LIB
 
@@ -135,6 +137,14 @@ def set_option(key: str, value: int) -> None:
 
 def get_option(key: str) -> int:
     return lib().smfft_get_option(key.encode())
+
+
+def twiddle_table() -> int:
+    """device address of the W_8192 table (for smfft::BlockFFT<..., TW_LUT> in user kernels)"""
+    p = lib().smfft_twiddle_table()
+    if not p:
+        raise SmfftError(lib().smfft_last_error().decode())
+    return int(p)
 
 
 def launch_count() -> int:

@@ -293,6 +293,12 @@ int smfft_init(void)
     return get_device_state(&ds);
 }
 
+const void* smfft_twiddle_table(void)
+{
+    DeviceState* ds = nullptr;
+    return get_device_state(&ds) ? nullptr : (const void*)ds->tw;
+}
+
 int smfft_set_stream(void* stream)
 {
     t_stream = (cudaStream_t)stream;

@@ -10,7 +10,9 @@ NVCC = "/usr/local/cuda/bin/nvcc"
 
 def build() -> str:
     src = os.path.join(HERE, "compat_kernels.cu")
-    deps = [src, os.path.join(ROOT, "include", "smfft", "compat.cuh"), os.path.join(ROOT, "include", "smfft", "detail", "block_fft.cuh")]
+    import glob
+
+    deps = [src] + glob.glob(os.path.join(ROOT, "include", "smfft", "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "smfft", "detail", "*.cuh"))
     if os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
     if not os.path.exists(NVCC):

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "smfft/compat.cuh"
+#include "smfft/device.cuh"
 
 #define CT_CASE(N, KERNEL)                                                                                     \
     case N:                                                                                                    \
@@ -138,5 +139,89 @@ __global__ void user_convolve(const float2* x, const float2* H, float2* y)
 extern "C" int compat_user_convolve_1024(const float2* x, const float2* H, float2* y, int nffts)
 {
     user_convolve<FFT_1024_forward, FFT_1024_inverse><<<nffts, 256>>>(x, H, y);
+    return (int)cudaGetLastError();
+}
+
+// ---- the NATIVE device primitive (include/smfft/device.cuh): 16 points per thread, data in registers across the call ----
+
+template <class FFT>
+__global__ void __launch_bounds__(FFT::THREADS) native_fft(const float2* x, float2* y, const float2* w8192)
+{
+    __shared__ __align__(16) float2 xch[FFT::EXCHANGE_POINTS];
+    __shared__ float2 tw[FFT::TWIDDLE_POINTS + 1];
+    if (FFT::TWIDDLE_POINTS) {
+        FFT::fill_twiddles(tw, w8192);
+        __syncthreads();
+    }
+    float2 v[FFT::R];
+    const size_t base = (size_t)blockIdx.x * FFT::TILE_POINTS;
+    FFT::load(v, x + base);
+    FFT::exec(v, xch, tw);
+    FFT::store(v, y + base);
+}
+
+// lut != 0: table twiddles (w8192 = smfft_twiddle_table()), else MUFU; r32 != 0: 32 points per thread
+extern "C" int native_fft_launch(const float2* x, float2* y, int n, int nffts, int inverse, int lut, const float2* w8192)
+{
+#define NF(E, F)                                                                                                                    \
+    case (1 << E): {                                                                                                                \
+        const int grid = nffts / F;                                                                                                 \
+        if (!inverse && !lut) native_fft<smfft::BlockFFT<E, smfft::FORWARD, F>><<<grid, smfft::BlockFFT<E, 0, F>::THREADS>>>(x, y, w8192);              \
+        if (inverse && !lut) native_fft<smfft::BlockFFT<E, smfft::INVERSE, F>><<<grid, smfft::BlockFFT<E, 0, F>::THREADS>>>(x, y, w8192);               \
+        if (!inverse && lut) native_fft<smfft::BlockFFT<E, smfft::FORWARD, F, smfft::TW_LUT>><<<grid, smfft::BlockFFT<E, 0, F>::THREADS>>>(x, y, w8192); \
+        if (inverse && lut) native_fft<smfft::BlockFFT<E, smfft::INVERSE, F, smfft::TW_LUT>><<<grid, smfft::BlockFFT<E, 0, F>::THREADS>>>(x, y, w8192);  \
+        break;                                                                                                                      \
+    }
+    switch (n) {
+        NF(5, 32) NF(6, 16) NF(7, 8) NF(8, 4) NF(9, 2) NF(10, 2) NF(11, 1) NF(12, 1)
+        default: return -1;
+    }
+#undef NF
+    return (int)cudaGetLastError();
+}
+
+// the convolution use case on the native primitive: load -> forward -> multiply by H (in registers) -> inverse -> store
+template <int E, int F, int TW>
+__global__ void __launch_bounds__(smfft::BlockFFT<E, 0, F>::THREADS) native_convolve(const float2* x, const float2* H, float2* y, const float2* w8192)
+{
+    using FWD = smfft::BlockFFT<E, smfft::FORWARD, F, TW>;
+    using INV = smfft::BlockFFT<E, smfft::INVERSE, F, TW>;
+    __shared__ __align__(16) float2 xch[FWD::EXCHANGE_POINTS];
+    __shared__ float2 twf[FWD::TWIDDLE_POINTS + 1], twi[FWD::TWIDDLE_POINTS + 1];
+    if (FWD::TWIDDLE_POINTS) {
+        FWD::fill_twiddles(twf, w8192);
+        INV::fill_twiddles(twi, w8192);
+        __syncthreads();
+    }
+    float2 v[FWD::R];
+    const size_t base = (size_t)blockIdx.x * FWD::TILE_POINTS;
+    FWD::load(v, x + base);
+    smfft::block_convolve<FWD, INV>(v, xch, [&](float2 a, int k) {
+        const float2 h = __ldg(H + k);
+        constexpr float sc = 1.0f / (float)FWD::N;
+        return make_float2((a.x * h.x - a.y * h.y) * sc, (a.x * h.y + a.y * h.x) * sc);
+    }, twf, twi);
+    INV::store(v, y + base);
+}
+
+extern "C" int native_convolve_launch(const float2* x, const float2* H, float2* y, int n, int nffts, int lut, const float2* w8192)
+{
+    switch (n) {
+        case 256: if (lut) native_convolve<8, 4, smfft::TW_LUT><<<nffts / 4, 64>>>(x, H, y, w8192); else native_convolve<8, 4, smfft::TW_MUFU><<<nffts / 4, 64>>>(x, H, y, w8192); break;
+        case 1024: if (lut) native_convolve<10, 2, smfft::TW_LUT><<<nffts / 2, 128>>>(x, H, y, w8192); else native_convolve<10, 2, smfft::TW_MUFU><<<nffts / 2, 128>>>(x, H, y, w8192); break;
+        case 4096: if (lut) native_convolve<12, 1, smfft::TW_LUT><<<nffts, 256>>>(x, H, y, w8192); else native_convolve<12, 1, smfft::TW_MUFU><<<nffts, 256>>>(x, H, y, w8192); break;
+        default: return -1;
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int compat_user_convolve(const float2* x, const float2* H, float2* y, int n, int nffts)
+{
+    switch (n) {
+        case 256: user_convolve<FFT_256_forward, FFT_256_inverse><<<nffts, 64>>>(x, H, y); break;
+        case 1024: user_convolve<FFT_1024_forward, FFT_1024_inverse><<<nffts, 256>>>(x, H, y); break;
+        case 4096: user_convolve<FFT_4096_forward, FFT_4096_inverse><<<nffts, 1024>>>(x, H, y); break;
+        default: return -1;
+    }
     return (int)cudaGetLastError();
 }

@@ -22,6 +22,27 @@ int emu_run_compat(const void* in, void* out, int e, long long n_ffts, int mode,
     return -1;
 }
 
+void emu_set_compat_misalign(int float2s) { compat_tile_misalign() = float2s ? 1 : 0; }
+
+// the reference-contract C2C device function (compat::ct_dit, i.e. do_SMFFT_CT_DIT) with `reps` in-place repetitions;
+// also reports the bank-conflict factor of its shared-memory accesses and the warp shuffles of one block
+int emu_run_compat_ct(const void* in, void* out, int e, long long n_ffts, int dir, int reorder, int reps, double* bank_factor,
+                      long long* shuffles)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+#define CT(E)                                                                                                        \
+    if (e == E) {                                                                                                    \
+        if (dir == 0 && reorder == 1) return run_compat_ct<E, 0, 1>(i, o, n_ffts, reps, bank_factor, shuffles);      \
+        if (dir == 0 && reorder == 0) return run_compat_ct<E, 0, 0>(i, o, n_ffts, reps, bank_factor, shuffles);      \
+        if (dir == 1 && reorder == 1) return run_compat_ct<E, 1, 1>(i, o, n_ffts, reps, bank_factor, shuffles);      \
+        if (dir == 1 && reorder == 0) return run_compat_ct<E, 1, 0>(i, o, n_ffts, reps, bank_factor, shuffles);      \
+    }
+    CT(5) CT(6) CT(7) CT(8) CT(9) CT(10) CT(11) CT(12)
+#undef CT
+    return -1;
+}
+
 // alternative shapes: exercise the generic pass machinery (other radices, tile sizes, stage counts)
 int emu_run_alt(const void* in, void* out, int variant, long long n_ffts, int dir, int reorder, int io, int tw, int grid,
                 double* bank_factor)

@@ -106,6 +106,9 @@ void launch(int grid, int threads, size_t smem_bytes, const std::function<void(u
         blk.done.assign(threads, 0);
         blk.alive = threads;
         blk.log.resize(threads);
+        blk.shfl_val.assign(threads, 0.0f);
+        blk.warp_arrived.assign((threads + 31) / 32, 0);
+        blk.warp_gen.assign((threads + 31) / 32, 0);
         blk.record = stats != nullptr && bid == 0;
         void* raw = nullptr;
         if (posix_memalign(&raw, 1024, smem_bytes + 1024)) abort();

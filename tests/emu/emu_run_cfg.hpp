@@ -2,6 +2,7 @@
 #pragma once
 #include "emu_runtime.hpp"
 
+#include "smfft/detail/compat_core.cuh"
 #include "kernels.cuh"
 #include "tuning.hpp"
 
@@ -72,11 +73,53 @@ inline int run_shape(const float2* in, float2* out, long long n_ffts, int dir, i
     return -1;
 }
 
-// the configuration behind include/smfft/compat.cuh (reference thread contract: 4 points per thread,
-// linear tile, swizzled exchanges, MUFU twiddles, 8-byte shared accesses)
+// the engines behind include/smfft/compat.cuh (reference thread contract: 4 points per thread, linear tile, MUFU twiddles):
+// C2C goes through compat::ct_dit -- the very dispatch do_SMFFT_CT_DIT<P> calls -- inside a wrapper with the reference's
+// load / sync / FFT / sync / store skeleton; R2C / C2R through the block FFT configuration the Stockham wrappers use
+// tests can push the tile off its 16-byte alignment (README.md:12 of the reference asks for none): one float2
+inline int& compat_tile_misalign()
+{
+    static int m = 0;
+    return m;
+}
+
+template <int E, int DIR, int REORDER>
+inline int run_compat_ct(const float2* in, float2* out, long long n_ffts, int reps, double* bank_factor, long long* shuffles)
+{
+    constexpr int F = E < 7 ? (128 >> E) : 1, L = F << E, T = L / 4;
+    if (n_ffts % F) return -2;
+    emu::BankStats st;
+    const long long n_tiles = n_ffts / F;
+    emu::launch((int)n_tiles, T, (size_t)L * 8 + 64,
+                [&](unsigned char* smem) {
+                    float2* s = reinterpret_cast<float2*>(smem) + compat_tile_misalign();
+                    const int tid = plat::tid();
+                    const long long base = (long long)plat::bid() * L;
+                    if (reps == 0) {  // the body of the external wrapper kernel: tile in global memory
+                        compat::ct_dit_external<E, F, DIR, REORDER>(s, in + base, out + base);
+                        if (shuffles && tid == 0 && plat::bid() == 0) *shuffles = emu::g_blk->shuffles;
+                        return;
+                    }
+                    for (int q = 0; q < 4; q++) plat::sts64(s + tid + q * T, in[base + tid + q * T]);
+                    plat::sync_block();
+                    for (int r = 0; r < reps; r++) {
+                        compat::ct_dit<E, F, DIR, REORDER>(s);
+                        plat::sync_block();
+                    }
+                    for (int q = 0; q < 4; q++) out[base + tid + q * T] = plat::lds64(s + tid + q * T);
+                    if (shuffles && tid == 0 && plat::bid() == 0) *shuffles = emu::g_blk->shuffles;
+                },
+                bank_factor ? &st : nullptr);
+    if (bank_factor) *bank_factor = st.factor();
+    return 0;
+}
+
 template <int E, int MODE, int DIR, int REORDER>
 inline int run_compat(const float2* in, float2* out, long long n_ffts, double* bank_factor)
 {
+    if constexpr (MODE == kernels::MODE_C2C) {
+        return run_compat_ct<E, DIR, REORDER>(in, out, n_ffts, 1, bank_factor, nullptr);
+    } else {
     using C = detail::BlockCfg<E, 2, (E < 7 ? (128 >> E) : 1), DIR, REORDER, TW_MUFU, detail::LayoutLinear, detail::LayoutSW128, false>;
     kernels::TileArgs args;
     const long long n_points = n_ffts * C::N;
@@ -92,5 +135,5 @@ inline int run_compat(const float2* in, float2* out, long long n_ffts, double* b
                 bank_factor ? &st : nullptr);
     if (bank_factor) *bank_factor = st.factor();
     return 0;
+    }
 }
-

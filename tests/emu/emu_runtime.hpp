@@ -16,6 +16,7 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -68,6 +69,10 @@ struct Block {
     std::vector<char> done;
     ucontext_t sched;
     int arrived = 0, alive = 0, gen = 0;
+    // warp-level exchange state (shfl_xor / sync_warp): values parked per lane, a generation barrier per warp
+    std::vector<float> shfl_val;
+    std::vector<int> warp_arrived, warp_gen;
+    long long shuffles = 0;
     unsigned char* smem = nullptr;
     size_t smem_bytes = 0;
     std::vector<TmaOp> queue;
@@ -103,6 +108,35 @@ inline void sync_block()
         while (b->gen == gen) emu::yield();
     }
 }
+
+// all live lanes of the calling thread's warp (the kernels here never exit part of a warp early)
+inline void sync_warp()
+{
+    emu::Block* b = emu::g_blk;
+    const int w = b->cur / 32;
+    const int lanes = std::min(32, b->nthreads - 32 * w);
+    const int gen = b->warp_gen[w];
+    if (++b->warp_arrived[w] == lanes) {
+        b->warp_arrived[w] = 0;
+        b->warp_gen[w]++;
+    } else {
+        while (b->warp_gen[w] == gen) emu::yield();
+    }
+}
+inline float shfl_xor(float v, int mask)
+{
+    emu::Block* b = emu::g_blk;
+    const int me = b->cur;
+    b->shfl_val[me] = v;
+    sync_warp();  // every lane has parked its value
+    const int src = (me & ~31) | ((me ^ mask) & 31);
+    const float r = src < b->nthreads ? b->shfl_val[src] : v;
+    sync_warp();  // every lane has read before the slot is reused
+    if ((me & 31) == 0) b->shuffles++;
+    return r;
+}
+
+inline unsigned smem_addr(const void* p) { return (unsigned)((const unsigned char*)p - emu::g_blk->smem); }
 
 inline void rec(const void* p, int width, int store)
 {

@@ -26,6 +26,7 @@ def emu():
     lib.emu_run.argtypes = [P, P, I, LL, I, I, I, I, I, I, I, D]
     lib.emu_run_alt.argtypes = [P, P, I, LL, I, I, I, I, I, D]
     lib.emu_run_compat.argtypes = [P, P, I, LL, I, I, I, D]
+    lib.emu_run_compat_ct.argtypes = [P, P, I, LL, I, I, I, D, ctypes.POINTER(ctypes.c_longlong)]
     lib.emu_run_late.argtypes = [P, P, I, LL, I]
     lib.emu_run_dual.argtypes = [P, P, I, I, LL, I, I, I, I, I, D]
     return lib
@@ -187,6 +188,49 @@ def test_reference_device_api_configuration(emu, e):
     out = np.zeros_like(h)
     assert emu.emu_run_compat(h.ctypes.data, out.ctypes.data, e, 8, 2, 1, 1, None) == 0
     assert O.rel_l2(out.view(np.float32), O.c2r_packed_fp64(h)) < TOL
+
+
+@pytest.mark.parametrize("e", range(5, 13))
+def test_reference_device_api_engines(emu, e):
+    """compat::ct_dit -- the dispatch behind do_SMFFT_CT_DIT<P> -- and compat::ct_dit_external -- the body of
+    SMFFT_DIT_external<P> -- on the emulator: warp-shuffle engines for one-warp tiles and for fft_reorder = 0, Stockham
+    passes for natural order above 128 points.  Values vs FP64, three in-place repetitions (the SMFFT_DIT_multiple loop),
+    the bank-conflict factor of the shared-memory accesses and the number of warp shuffles per tile."""
+    n = 1 << e
+    nf = 8
+    x = O.uniform_c64(nf, n, seed=e)
+    warps = max(1, n // 128)
+    for direction, reorder in ((0, 1), (0, 0), (1, 1), (1, 0)):
+        want = O.ct_c2c_fp64(x, bool(direction), bool(reorder))
+        for reps in (1, 0):                      # 1: tile in shared memory (device function), 0: tile in global memory (external wrapper)
+            out = np.zeros_like(x)
+            bank = ctypes.c_double(0)
+            sh = ctypes.c_longlong(0)
+            assert emu.emu_run_compat_ct(x.ctypes.data, out.ctypes.data, e, nf, direction, reorder, reps, ctypes.byref(bank), ctypes.byref(sh)) == 0
+            assert O.rel_l2(out, want) < TOL, (e, direction, reorder, reps)
+            if not reorder and reps == 1:
+                # fft_reorder = 0: every access conflict-free except the final LINEAR store of 2048 / 4096 points (2 / 4 wavefronts)
+                assert bank.value <= {11: 1.17, 12: 1.51}.get(e, 1.0) + 1e-9, (e, bank.value)
+            if e <= 7:
+                assert bank.value <= 1.25 + 1e-9       # natural order: the bit-reversed store of 32 / 128 points pays 2 wavefronts
+                assert sh.value == {5: 12, 6: 12, 7: 16}[e]  # float shuffles per thread: 6 per 4x4 transposition, 4 per bit swap
+        if not reorder:
+            # a tile that is only 8-byte aligned takes the 64-bit first read (rotated rows): same values, still conflict-free
+            emu.emu_set_compat_misalign(1)
+            out = np.zeros_like(x)
+            bank = ctypes.c_double(0)
+            assert emu.emu_run_compat_ct(x.ctypes.data, out.ctypes.data, e, nf, direction, reorder, 1, ctypes.byref(bank), None) == 0
+            emu.emu_set_compat_misalign(0)
+            assert O.rel_l2(out, want) < TOL
+            assert bank.value <= {11: 1.17, 12: 1.51}.get(e, 1.0) + 1e-9, (e, bank.value)
+        xs = (x / np.float32(n)).astype(np.complex64)
+        out = np.zeros_like(xs)
+        assert emu.emu_run_compat_ct(xs.ctypes.data, out.ctypes.data, e, nf, direction, reorder, 3, None, None) == 0
+        w = xs.astype(np.complex128)
+        for _ in range(3):
+            w = O.ct_c2c_fp64(w, bool(direction), bool(reorder))
+        assert O.rel_l2(out, w) < TOL
+    assert warps >= 1
 
 
 @pytest.mark.parametrize("variant,e,kind", [(0, 12, "c2c_fwd_r"), (1, 12, "c2c_inv_n"), (2, 10, "c2c_fwd_n"), (3, 8, "c2c_fwd_r"),

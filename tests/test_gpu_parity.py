@@ -261,6 +261,11 @@ def compat():
     lib.compat_stockham_external.argtypes = [P, P, I, I]
     lib.compat_r2c_c2r_external.argtypes = [P, P, I, I, I]
     lib.compat_user_convolve_1024.argtypes = [P, P, P, I]
+    lib.compat_user_convolve.argtypes = [P, P, P, I, I]
+    lib.compat_stockham_multiple.argtypes = [P, P, I, I]
+    lib.compat_r2c_multiple.argtypes = [P, P, I, I]
+    lib.native_fft_launch.argtypes = [P, P, I, I, I, I, P]
+    lib.native_convolve_launch.argtypes = [P, P, P, I, I, I, P]
     return lib
 
 
@@ -592,3 +597,55 @@ def test_python_wrappers_check_their_buffers(sm):
         sm.exec_c2c(x.cpu(), y, 1024, 100, False, True)
     with pytest.raises(sm.SmfftError, match="fft|FFT"):
         sm.pipeline_host(x.cpu(), y.cpu(), 0, 10)                  # validated before it is used as a divisor
+
+
+# ---- the native device primitive (include/smfft/device.cuh) used from a user program ------------------------------------
+
+@pytest.mark.parametrize("n", SIZES)
+def test_native_device_primitive(sm, compat, n):
+    """smfft::BlockFFT<log2 N, dir, FFTS, TW>::load / exec / store inside a user kernel (tests/compat/compat_kernels.cu):
+    registers in, registers out, natural order, both directions, MUFU and table twiddles."""
+    nf = 64
+    x = O.uniform_c64(nf, n, seed=n + 23)
+    dx = to_dev(x)
+    tw = sm.twiddle_table()
+    for inverse in (0, 1):
+        want = O.ct_c2c_fp64(x, bool(inverse), True)
+        for lut in (0, 1):
+            dy = torch.zeros_like(dx)
+            assert compat.native_fft_launch(dx.data_ptr(), dy.data_ptr(), n, nf, inverse, lut, tw) == 0
+            torch.cuda.synchronize()
+            assert O.rel_l2(c64(dy), want) < TOL, (n, inverse, lut)
+            assert O.rel_l2(c64(dy), O.c_ct_c2c(x, bool(inverse), True)) < TOL
+
+
+@pytest.mark.parametrize("n", [256, 1024, 4096])
+def test_native_fused_convolution(sm, compat, n):
+    """smfft::block_convolve: forward transform, pointwise functor on the registers, inverse transform, one launch -- and the
+    same convolution through the drop-in device function (compat) for every size the bench times."""
+    nf = 48
+    x = O.uniform_c64(nf, n, seed=n + 29)
+    rng = np.random.default_rng(n)
+    h = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    dx, dh = to_dev(x), to_dev(h)
+    want = np.fft.ifft(np.fft.fft(x.astype(np.complex128), axis=-1) * h.astype(np.complex128), axis=-1)
+    tw = sm.twiddle_table()
+    for lut in (0, 1):
+        dy = torch.zeros_like(dx)
+        assert compat.native_convolve_launch(dx.data_ptr(), dh.data_ptr(), dy.data_ptr(), n, nf, lut, tw) == 0
+        torch.cuda.synchronize()
+        assert O.rel_l2(c64(dy), want) < TOL, (n, lut)
+    dy = torch.zeros_like(dx)
+    assert compat.compat_user_convolve(dx.data_ptr(), dh.data_ptr(), dy.data_ptr(), n, nf) == 0
+    torch.cuda.synchronize()
+    assert O.rel_l2(c64(dy), want) < TOL
+
+
+def test_compat_multiple_wrappers_run(compat):
+    """FFT_GPU_multiple / FFT_GPU_R2C_C2R_multiple by the reference's names and launch shapes (timing-only kernels)."""
+    big = torch.rand((400 * 4096, 2), device="cuda")
+    out = torch.empty_like(big)
+    for n in (256, 1024, 4096):
+        assert compat.compat_stockham_multiple(big.data_ptr(), out.data_ptr(), n, 400) == 0
+        assert compat.compat_r2c_multiple(big.data_ptr(), out.data_ptr(), n, 400) == 0
+    torch.cuda.synchronize()
