@@ -178,7 +178,7 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # reported GPU baselines (outside the timed region, rank 0): recompiled reference kernels, cuFFT
 # ----------------------------------------------------------------------------------------------
-def sustained_arm(launchers, steps, warmup=2):
+def sustained_arm(launchers, steps, warmup=3):
     """The protocol of the timed region, for any arm: `steps` back-to-back passes over the whole launcher list (the
     16-launch step), every launch between two CUDA events on the launching stream; per key the median / min over the
     steps.  launchers: [(key, callable)]; a key may repeat inside a step (cuFFT has no no-reorder mode)."""
@@ -204,7 +204,7 @@ def sustained_arm(launchers, steps, warmup=2):
     return out
 
 
-def reference_gpu_baseline(x, y, steps=5):
+def reference_gpu_baseline(x, y, steps=5, warmup=3):
     """the reference's own kernels rebuilt for sm_100a (oracle/_ref), through ITS FFT_external_benchmark (CT:583), in the
     same sustained 16-launch step as the product"""
     import ctypes
@@ -221,14 +221,14 @@ def reference_gpu_baseline(x, y, steps=5):
         xp, yp = x.data_ptr(), y.data_ptr()
         launchers = [(f"{n}{'r' if reorder else 'n'}", (lambda n=n, reorder=reorder: fn(xp, yp, n, BATCH_POINTS // n, False, bool(reorder), ctypes.byref(ms))))
                      for n, reorder in configs()]
-        out = sustained_arm(launchers, steps)
-        out["how"] = "unmodified reference kernels (sm_100a rebuild), sustained 16-launch step, CUDA events per launch, median over %d steps" % steps
+        out = sustained_arm(launchers, steps, warmup)
+        out["how"] = "unmodified reference kernels (sm_100a rebuild), sustained 16-launch step, CUDA events per launch, median over %d steps after %d warm-up steps" % (steps, warmup)
         return out
     except Exception as ex:  # pragma: no cover
         return {"error": str(ex)[:200]}
 
 
-def cufft_baseline(x, y, steps=5):
+def cufft_baseline(x, y, steps=5, warmup=3):
     """cuFFT on the same buffers: plans created outside the timer, out of place, one cufftExecC2C per timed
     launch, in the same sustained 16-launch step as the product (cuFFT has no no-reorder mode: each size runs twice per step)."""
     import ctypes
@@ -250,8 +250,10 @@ def cufft_baseline(x, y, steps=5):
                 plans[n] = h
         xp, yp = ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr())
         launchers = [(str(n), (lambda n=n: lib.cufftExecC2C(plans[n], xp, yp, -1))) for n in SIZES if n in plans for _ in (0, 1)]
-        out = sustained_arm(launchers, steps)
-        out["how"] = "cufftPlan1d(C2C, batch) + cufftExecC2C, out of place, sustained 16-launch step (each size twice), CUDA events per launch, median over %d steps" % steps
+        out = sustained_arm(launchers, steps, warmup)
+        out["how"] = ("cufftPlan1d(C2C, batch) + cufftExecC2C, out of place, sustained 16-launch step (each size twice), CUDA events per launch, "
+                      "median over %d steps after %d warm-up steps -- the SAME step count and warm-up as the timed region (a burst shorter than ~50 ms runs "
+                      "at higher SM clocks than the steady state the headline is measured in, profiles/r02_burst_timeline_*.json)" % (steps, warmup))
         return out
     except Exception as ex:  # pragma: no cover
         return {"error": str(ex)[:200]}
@@ -492,8 +494,8 @@ def run_ours(args):
             cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
                    "sample": f"{reps} x {len(cfgs)} configs x {sample} complex points ({dt:.1f} s), oracle C restatement of CT:334-532 with OpenMP"}
         if not args.no_baselines:
-            baselines["reference_sm100a_ms"] = reference_gpu_baseline(x, y)
-            baselines["cufft_ms"] = cufft_baseline(x, y)
+            baselines["cufft_ms"] = cufft_baseline(x, y, args.steps, max(args.warmup, 3))
+            baselines["reference_sm100a_ms"] = reference_gpu_baseline(x, y, max(3, args.steps // 2), 2)
         if not args.no_device_api:
             device_api = device_api_leg(x, y)
     if world > 1:

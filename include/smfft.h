@@ -119,14 +119,21 @@ int smfft_pipeline_release(void);
 
 /* ---- knobs -------------------------------------------------------------------------------------
  * keys: "io" (0 = measured best TMA staging per size [default], 1 = LDG/STG staging by the threads,
- * 2 = TMA loads + TMA stores, 3 = TMA loads + stores from registers, 4 = register-direct input where an instance
- * exists [1024-point natural-order C2C], the default elsewhere), "twiddle" (0 = table+powers
+ * 2 = TMA loads + TMA stores, 3 = TMA loads + stores from registers, 4 / 5 = register-direct input, shape A / B, where an
+ * instance exists [natural-order C2C of 128..1024 points], the default elsewhere),
+ * "select" (0 = the static, sustained-load table of tuning.hpp [default]; 1 = first-use selection: the first out-of-place
+ * call of a transform on a batch of at least 2^"select_min_log2_points" [24] points times the table's instance against
+ * its alternates on that batch -- synchronously, a few dozen launches -- and the fastest serves that transform on that
+ * device from then on; smfft_select_report() lists the decisions, "select_reset" forgets them), "twiddle" (0 = table+powers
  * [default], 1 = MUFU __sincosf), "quirk_4096" (1 = reproduce FFT_4096_inverse_noreorder running
  * the forward transform, CT/SM_FFT_parameters.cuh:388; default 0 = mathematically correct),
  * "ctas_per_sm" (0 = built-in), "pipeline_chunk_mib" (default chunk of smfft_pipeline_host, 1..1024, default 128), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
  * of shared memory), "device_sms" (read-only). */
 int smfft_set_option(const char* key, int value);
 int smfft_get_option(const char* key);
+/* the first-use selection's decisions on the current device as text, one line per transform with every candidate's
+ * milliseconds; returns the number of bytes written into buf (NUL-terminated) */
+int smfft_select_report(char* buf, int cap);
 /* device address of the current device's twiddle table W_8192^j = exp(-2 pi i j / 8192), j = 0..8191 (float2, rounded
  * from FP64): what smfft::BlockFFT<..., TW_LUT>::fill_twiddles (include/smfft/device.cuh) reads.  NULL on failure. */
 const void* smfft_twiddle_table(void);

@@ -31,6 +31,7 @@
 #include "layout.cuh"
 #include "radix.cuh"
 #include "twiddle.cuh"
+#include "warp_xchg.cuh"
 
 namespace smfft {
 namespace detail {
@@ -42,7 +43,9 @@ namespace detail {
 // DUAL_    : bit flags.  2 = packed f32x2 add / subtract on (re, im) in the butterflies (same threads, fewer issue slots);
 //            4 = reversed pass plan (small radix first; lets the C2R pass own its pairs, see MirrorC2R);
 //            1 = one thread carries the same points of TWO transforms of the tile in the packed f32x2 lanes
-//            (block_fft_dual.cuh): half the threads, half the floating-point and exchange instructions per point.
+//            (block_fft_dual.cuh): half the threads, half the floating-point and exchange instructions per point;
+//            8 = two-pass plans of transforms held by 2 or 4 LANES (32 / 64 points at R = 16) exchange through warp
+//            shuffles instead of the tile (warp_xchg.cuh): no barrier, a third of the shared-memory traffic.
 template <int E_, int B_, int F_, int DIR_, int REORDER_, int TW_, class Layout_ = LayoutSW128, class XLayout_ = Layout_,
           bool VEC128_ = true, bool SKEW_ = true, int DUAL_ = 0>
 struct BlockCfg {
@@ -57,8 +60,10 @@ struct BlockCfg {
     static constexpr int DUAL = DUAL_ & 1;
     static constexpr int PACK = (DUAL_ >> 1) & 1;  // one transform per thread, packed (re, im) add / subtract in the butterflies
     static constexpr int REV = (DUAL_ >> 2) & 1;   // pass plan with the small radix FIRST: [2^(E mod B), R, .., R]
+    static constexpr int XSHFL = (DUAL_ >> 3) & 1;  // the one exchange of a two-pass plan by warp shuffles (T = 2 or 4 lanes per transform)
     static constexpr int THREADS = (F_ * T) >> DUAL;
-    static_assert(DUAL_ >= 0 && DUAL_ < 8 && (!REV || ((E_ % B_ == 3 || E_ % B_ == 2) && VEC128_)), "reversed plans: first radix 8 or 4");
+    static_assert(DUAL_ >= 0 && DUAL_ < 16 && (!REV || ((E_ % B_ == 3 || E_ % B_ == 2) && VEC128_)), "reversed plans: first radix 8 or 4");
+    static_assert(((DUAL_ >> 3) & 1) == 0 || ((DUAL_ & 5) == 0 && B_ == 4 && (E_ == 5 || E_ == 6)), "shuffle exchange: R = 16, 32 or 64 points, plan [16, T]");
     static_assert((DUAL_ & 1) == 0 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
                                  std::is_same<Layout_, LayoutSW128>::value && VEC128_),
                   "dual-lane transforms: an even number of transforms per tile, T >= 16, N >= 128, R >= 16, SW128 tile");
@@ -119,6 +124,55 @@ SMFFT_DEV void fill_twiddle_table(float2* stw, const float2* __restrict__ gtw, i
         }
     }
 }
+
+// The same fill in two phases for short-lived CTAs (register-direct kernels, one tile per CTA): the global reads are
+// ISSUED early (right after the CTA's own input loads) into registers, and only stored to the shared table later, behind
+// the first pass's arithmetic -- a table read that precedes the input loads costs such a CTA a whole memory round trip.
+// C2C tables only; K = entries per thread.
+template <class C>
+struct TwiddlePrefetch {
+    static constexpr int K = C::TW == TW_LUT ? (C::TW_C2C_ENTRIES + C::THREADS - 1) / C::THREADS : 0;
+    static constexpr bool OK = K >= 0 && K <= 4;
+    float2 w[K > 0 ? K : 1];
+    // entry i of the compact table = pass p (>= 1), index k inside it
+    static SMFFT_DEV void locate(int i, int& stride, bool& valid)
+    {
+        valid = false;
+        stride = 0;
+        static_for<C::P>([&](auto PI) {
+            constexpr int p = decltype(PI)::value;
+            if constexpr (p >= 1) {
+                constexpr int NS = 1 << C::ns_log2(p), WN = NS << C::radix_log2(p), OFF = C::tw_offset(p);
+                if (i >= OFF && i < OFF + NS) {
+                    valid = true;
+                    stride = (i - OFF) * (kTwiddleTableSize / WN);
+                }
+            }
+        });
+    }
+    SMFFT_DEV void load(const float2* __restrict__ gtw, int tid)
+    {
+        static_for<(K > 0 ? K : 0)>([&](auto KI) {
+            constexpr int j = decltype(KI)::value;
+            int stride;
+            bool valid;
+            locate(tid + j * C::THREADS, stride, valid);
+            w[j] = valid ? plat::ldg_ro(gtw + stride) : make_float2(1.0f, 0.0f);
+        });
+    }
+    SMFFT_DEV void store(float2* stw, int tid) const
+    {
+        static_for<(K > 0 ? K : 0)>([&](auto KI) {
+            constexpr int j = decltype(KI)::value;
+            const int i = tid + j * C::THREADS;
+            if (i < C::TW_C2C_ENTRIES) {
+                float2 x = w[j];
+                if (C::DIR) x.y = -x.y;
+                stw[i] = x;
+            }
+        });
+    }
+};
 
 // ---- tile <-> registers ------------------------------------------------------------------------
 
@@ -589,7 +643,29 @@ SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t
         fft_pass_compute_mirror<C>(v, t, tw);
     else
         fft_pass_compute<C, PIDX>(v, vt, tw);
-    if constexpr (PIDX + 1 < C::P) {
+    if constexpr (C::XSHFL && PIDX == 0) {
+        // Plan [16, T], T = 2 or 4 lanes per transform: output q of lane j belongs to lane q mod T, register (16/T) j + q div T.
+        // Per group i of T registers {v[iT + c]} that is a T x T transposition with the lanes, then a renaming.
+        static_assert(C::P == 2 && (C::T == 2 || C::T == 4) && C::R == 16, "shuffle exchange: plan [16, T]");
+        const int lane = plat::tid() & 31;
+        float2 w[C::R];
+        static_for<C::R / C::T>([&](auto II) {
+            constexpr int i = decltype(II)::value;
+            if constexpr (C::T == 4) {
+                float2 g[4] = {v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+                wf::xchg4<0, 1>(g, lane);
+                static_for<4>([&](auto JI) { w[(C::R / C::T) * decltype(JI)::value + i] = g[decltype(JI)::value]; });
+            } else {
+                const bool b = lane & 1;
+                const float2 send = b ? v[2 * i] : v[2 * i + 1];
+                const float2 got = wf::shfl_xor2(send, 1);
+                w[i] = b ? got : v[2 * i];                      // from lane 0: its v[2i + t]
+                w[(C::R / C::T) + i] = b ? v[2 * i + 1] : got;  // from lane 1
+            }
+        });
+        static_for<C::R>([&](auto MI) { v[decltype(MI)::value] = w[decltype(MI)::value]; });
+        run_passes<C, PIDX + 1, XF>(v, s, fbase, t, t, tw, hook);
+    } else if constexpr (PIDX + 1 < C::P) {
         plat::sync_block();  // every thread has finished reading the previous state of the tile
         if constexpr (PIDX == (std::remove_reference<Hook>::type::PASS < C::P - 2 ? std::remove_reference<Hook>::type::PASS : C::P - 2)) hook();
         using XL = typename ExchangeLayout<C, PIDX>::type;
@@ -892,15 +968,15 @@ SMFFT_DEV void load_global_natural(float2 (&v)[C::R], const float2* __restrict__
 
 // v = the thread's points of this tile (load_global_natural).  `s` may still be read by slower threads working
 // on the previous tile: the first barrier of run_passes orders that.
-template <class C, int XF>
+template <class C, int XF, class Hook = NoHook>
 SMFFT_DEV void block_fft_preloaded_to_global(float2 (&v)[C::R], float2* s, const float2* tw, float2* __restrict__ g,
-                                             long long valid)
+                                             long long valid, Hook&& hook = Hook{})
 {
     static_assert(C::REORDER == 1 && XF != XF_C2R, "register-direct input: natural-order C2C and R2C");
     const int tid = plat::tid();
     const int t = tid & (C::T - 1);
     const int fbase = (tid >> C::A) << C::E;
-    run_passes<C, 0, XF>(v, s, fbase, t, t, tw, NoHook{});
+    run_passes<C, 0, XF>(v, s, fbase, t, t, tw, hook);
     if constexpr (XF == XF_R2C) r2c_tail_regs<C>(v, s, tw);
     store_global_result<C, XF>(v, g, valid);
 }

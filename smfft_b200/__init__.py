@@ -23,6 +23,7 @@ from .api import (  # noqa: F401
     set_option,
     get_option,
     launch_count,
+    select_report,
     twiddle_table,
     lib,
     lib_path,

@@ -43,6 +43,7 @@ def lib() -> ctypes.CDLL:
             "smfft_exec_r2c_c2r_stream": [P, P, I, LL, I, P],
             "smfft_pipeline_release": [],
             "smfft_exec_repeated": [P, P, I, LL, I, I, I, I],
+            "smfft_select_report": [ctypes.c_char_p, I],
             "smfft_last_error_code": [],
             "smfft_stockham_external_benchmark": [P, P, I, LL, I, D],
             "smfft_stockham_multiple_benchmark": [P, P, I, LL, I, D],
@@ -145,6 +146,13 @@ def twiddle_table() -> int:
     if not p:
         raise SmfftError(lib().smfft_last_error().decode())
     return int(p)
+
+
+def select_report() -> str:
+    """the first-use selection's decisions on the current device (smfft_select_report)"""
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().smfft_select_report(buf, len(buf))
+    return buf.value.decode()
 
 
 def launch_count() -> int:

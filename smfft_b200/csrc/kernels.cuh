@@ -111,6 +111,8 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
 {
     constexpr int TILE_BYTES = C::L * 8;
     constexpr int ROWS = C::L / 16;  // 128-byte rows per tile
+    constexpr int BOX_ROWS = ROWS > 256 ? 256 : ROWS;  // a TMA box holds at most 256 rows: larger tiles (8192 points) move as several boxes
+    constexpr int NBOX = ROWS / BOX_ROWS;
     static_assert(TILE_BYTES % 1024 == 0, "tile must be a multiple of the 1 KB swizzle atom");
     static_assert(STAGES <= 8, "mbarrier block holds 8 barriers");
     const int tid = plat::tid();
@@ -119,7 +121,21 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
     // compact twiddle table, once per (persistent) CTA; made visible by the first barrier below
     constexpr int NBUF = io_uses_tma(IO) ? STAGES : 1;
     float2* stw = reinterpret_cast<float2*>(smem + NBUF * TILE_BYTES + 64);
-    detail::fill_twiddle_table<C, MODE != MODE_C2C, MODE == MODE_C2R>(stw, args.tw, tid, C::THREADS);
+    // register-direct, one tile per CTA: the CTA lives for a few microseconds, so its own input loads go out FIRST and
+    // the table fill (a global-memory round trip of its own) overlaps them instead of preceding them
+    constexpr bool EARLY_LOAD = IO == IO_REG && PF < 0;
+    // ... and where the plan has a pass behind which the table's stores can hide (C2C, at least two passes, few entries per
+    // thread) the table's own global reads are issued next and parked in registers until the first exchange (TwiddlePrefetch)
+    constexpr bool SPLIT_FILL = EARLY_LOAD && MODE == MODE_C2C && C::TW == TW_LUT && C::P >= 2 && detail::TwiddlePrefetch<C>::OK;
+    float2 v0[EARLY_LOAD ? C::R : 1];
+    detail::TwiddlePrefetch<C> twp;
+    if constexpr (EARLY_LOAD) {
+        if (my_tiles > 0) detail::load_global_natural<C>(v0, args.gin + first * C::L, args.n_points - first * C::L);
+    }
+    if constexpr (SPLIT_FILL)
+        twp.load(args.tw, tid);
+    else
+        detail::fill_twiddle_table<C, MODE != MODE_C2C, MODE == MODE_C2R>(stw, args.tw, tid, C::THREADS);
 
     if constexpr (IO == IO_TMA || IO == IO_TMA_STG) {
         uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * TILE_BYTES);
@@ -128,10 +144,14 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
         auto issue_load = [&](long long k) {
             uint64_t* bar = &full[k % STAGES];
             plat::mbar_arrive_expect_tx(bar, TILE_BYTES);
-            if (args.l2_hint & 1)
-                plat::tma_load_2d_hint(stage_ptr(k), &args.in_map, 0, (int)((first + k * step) * ROWS), bar, pol);
-            else
-                plat::tma_load_2d(stage_ptr(k), &args.in_map, 0, (int)((first + k * step) * ROWS), bar);
+            for (int b = 0; b < NBOX; b++) {
+                float2* dst = stage_ptr(k) + b * (BOX_ROWS * 16);
+                const int row = (int)((first + k * step) * ROWS) + b * BOX_ROWS;
+                if (args.l2_hint & 1)
+                    plat::tma_load_2d_hint(dst, &args.in_map, 0, row, bar, pol);
+                else
+                    plat::tma_load_2d(dst, &args.in_map, 0, row, bar);
+            }
         };
         if (tid == 0) {
             for (int i = 0; i < STAGES; i++) plat::mbar_init(&full[i], 1);
@@ -163,10 +183,13 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
                 plat::fence_proxy_async();
                 plat::sync_block();
                 if (tid == 0) {
-                    if (args.l2_hint & 2)
-                        plat::tma_store_2d_hint(&args.out_map, 0, (int)((first + k * step) * ROWS), s, pol);
-                    else
-                        plat::tma_store_2d(&args.out_map, 0, (int)((first + k * step) * ROWS), s);
+                    for (int b = 0; b < NBOX; b++) {
+                        const int row = (int)((first + k * step) * ROWS) + b * BOX_ROWS;
+                        if (args.l2_hint & 2)
+                            plat::tma_store_2d_hint(&args.out_map, 0, row, s + b * (BOX_ROWS * 16), pol);
+                        else
+                            plat::tma_store_2d(&args.out_map, 0, row, s + b * (BOX_ROWS * 16));
+                    }
                     plat::bulk_commit();
                 }
             }
@@ -193,14 +216,20 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
     } else if constexpr (IO == IO_REG) {
         static_assert(REPS == 1, "register-direct input is an external-benchmark path");
         float2* s = reinterpret_cast<float2*>(smem);
-        plat::sync_block();  // twiddle table
+        if constexpr (!SPLIT_FILL) plat::sync_block();  // twiddle table
         auto tile_base = [&](long long k) { return (first + k * step) * C::L; };
         if constexpr (PF < 0) {
             for (long long k = 0; k < my_tiles; k++) {
                 const long long p0 = tile_base(k);
-                float2 v[C::R];
-                detail::load_global_natural<C>(v, args.gin + p0, args.n_points - p0);
-                detail::block_fft_preloaded_to_global<C, MODE>(v, s, stw, args.gout + p0, args.n_points - p0);
+                if (k > 0) detail::load_global_natural<C>(v0, args.gin + p0, args.n_points - p0);  // tile 0 was loaded before the table fill
+                if constexpr (SPLIT_FILL) {
+                    // the table lands in shared memory between the two barriers of the first exchange: pass 0 uses no
+                    // twiddles, pass 1 reads them behind the second barrier (stored once: the first tile of the CTA)
+                    auto park = [&]() { if (k == 0) twp.store(stw, tid); };
+                    detail::block_fft_preloaded_to_global<C, MODE>(v0, s, stw, args.gout + p0, args.n_points - p0, detail::hook_at<0>(park));
+                } else {
+                    detail::block_fft_preloaded_to_global<C, MODE>(v0, s, stw, args.gout + p0, args.n_points - p0);
+                }
             }
         } else {
             // software pipeline, unrolled by two so the register sets swap roles without moves

@@ -118,27 +118,46 @@ static int get_device_state(DeviceState** out)
     return 0;
 }
 
-// io: kernels::IO_* or -1 = the preferred TMA staging of this size and mode
-static const KernelEntry* find_entry(int mode, int e, int dir, int reorder, int io, int tw, int reps)
+static EntryList entries_of(int e)
 {
-    EntryList l{nullptr, 0};
     switch (e) {
-        case 5: l = entries_e5(); break;
-        case 6: l = entries_e6(); break;
-        case 7: l = entries_e7(); break;
-        case 8: l = entries_e8(); break;
-        case 9: l = entries_e9(); break;
-        case 10: l = entries_e10(); break;
-        case 11: l = entries_e11(); break;
-        case 12: l = entries_e12(); break;
-        default: return nullptr;
+        case 5: return entries_e5();
+        case 6: return entries_e6();
+        case 7: return entries_e7();
+        case 8: return entries_e8();
+        case 9: return entries_e9();
+        case 10: return entries_e10();
+        case 11: return entries_e11();
+        case 12: return entries_e12();
+        case 13: return entries_e13();
+        default: return EntryList{nullptr, 0};
     }
+}
+
+// io: kernels::IO_* or -1 = the preferred staging of this size and mode; variant: 0 = the static table's instance,
+// 1 / 2 = alternates (register-direct shapes A / B, alternate TMA shapes)
+static const KernelEntry* find_entry(int mode, int e, int dir, int reorder, int io, int tw, int reps, int variant = 0)
+{
+    const EntryList l = entries_of(e);
     for (int i = 0; i < l.count; i++) {
         const KernelEntry& k = l.entries[i];
         if (k.mode != mode || k.dir != dir || k.reorder != reorder || k.tw != tw || k.reps != reps) continue;
-        if (io >= 0 ? k.io == io : k.prefer) return &k;
+        if (io >= 0 ? (k.io == io && k.variant == variant) : (k.prefer != 0)) return &k;
     }
     return nullptr;
+}
+
+// the alternates of one transform: candidates of the first-use selection (besides the static table's instance)
+static int find_alternates(int mode, int e, int dir, int reorder, int tw, int reps, const KernelEntry** out, int cap)
+{
+    const EntryList l = entries_of(e);
+    int n = 0;
+    for (int i = 0; i < l.count && n < cap; i++) {
+        const KernelEntry& k = l.entries[i];
+        if (k.mode != mode || k.dir != dir || k.reorder != reorder || k.tw != tw || k.reps != reps) continue;
+        if (!k.prefer && (k.variant >= 1 || k.tma_best)) out[n++] = &k;
+    }
+    return n;
 }
 
 static int make_map(CUtensorMap* m, const void* base, long long rows, int box_rows)
@@ -155,26 +174,10 @@ static int ilog2_exact(int n)
     return -1;
 }
 
-// launch one batch on `stream`: n_points complex points = whole transforms of 2^e points each
-static int launch_batch(int mode, int e, int dir, int reorder, int reps, const void* d_in, void* d_out, long long n_points,
-                        cudaStream_t stream)
+// launch one kernel instance over the batch on `stream`
+static int launch_entry(DeviceState* ds, const KernelEntry* k, const void* d_in, void* d_out, long long n_points, cudaStream_t stream)
 {
-    DeviceState* ds = nullptr;
-    if (get_device_state(&ds)) return 1;
-    if (n_points <= 0) return 0;
-    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail("smfft: device pointers must be 16-byte aligned");
-    const int opt_io = g_opt_io.load(), opt_tw = g_opt_tw.load(), opt_ctas = g_opt_ctas_per_sm.load(), opt_carve = g_opt_carveout.load();
-    int io = reps > 1 ? kernels::IO_LDG
-                      : opt_io == 0 ? -1 : opt_io == 1 ? kernels::IO_LDG : opt_io == 2 ? kernels::IO_TMA
-                      : opt_io == 3 ? kernels::IO_TMA_STG : kernels::IO_REG;
-    const KernelEntry* k = find_entry(mode, e, dir, reorder, io, opt_tw, reps);
-    if (!k && io == kernels::IO_REG) k = find_entry(mode, e, dir, reorder, -1, opt_tw, reps);  // no register-direct instance: the default one
-    if (!k && io == kernels::IO_TMA_STG) k = find_entry(mode, e, dir, reorder, kernels::IO_TMA, opt_tw, reps);
-    if (k && kernels::io_uses_tma(k->io) && n_points < k->tile_points)  // batch smaller than one tile: thread staging, no tensor map
-        k = find_entry(mode, e, dir, reorder, kernels::IO_LDG, opt_tw, reps);
-    if (k) io = k->io;
-    if (!k) return fail("smfft: no kernel instance for mode %d, 2^%d points, dir %d, reorder %d, io %d, tw %d, reps %d", mode, e, dir, reorder, io, opt_tw, reps);
-
+    const int opt_ctas = g_opt_ctas_per_sm.load(), opt_carve = g_opt_carveout.load();
     {
         std::lock_guard<std::mutex> lk(ds->mu);
         bool need_attr = true;
@@ -195,9 +198,10 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     args.gin = (const float2*)d_in;
     args.gout = (float2*)d_out;
     args.tw = ds->tw;
-    if (kernels::io_uses_tma(io)) {
-        if (make_map(&args.in_map, d_in, n_points / 16, k->tile_points / 16)) return 1;
-        if (io == kernels::IO_TMA && make_map(&args.out_map, d_out, n_points / 16, k->tile_points / 16)) return 1;
+    if (kernels::io_uses_tma(k->io)) {
+        const int box_rows = k->tile_points / 16 > 256 ? 256 : k->tile_points / 16;  // TMA boxes hold at most 256 rows (kernels.cuh splits larger tiles)
+        if (make_map(&args.in_map, d_in, n_points / 16, box_rows)) return 1;
+        if (k->io == kernels::IO_TMA && make_map(&args.out_map, d_out, n_points / 16, box_rows)) return 1;
     }
     // persistent grid: SMs x CTAs/SM.  The TMA kernels are launched with the measured load concurrency
     // (tuning.hpp), never more than fits; everything else fills the SM.
@@ -214,6 +218,123 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     CUDA_TRY(cudaLaunchKernel(k->func, dim3((unsigned)grid), dim3((unsigned)k->threads), params, (size_t)k->smem_bytes, stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
+}
+
+// ---- first-use selection (option "select" = 1) ----------------------------------------------------------------------
+// Where single launches and a long, power-capped run disagree about the best shape (tuning.hpp: 4096 points R = 32 vs
+// R = 16, register-direct vs TMA staging for 128..1024 points, one large vs six small CTAs at 32 points) no compile-time
+// table is right for every box and caller.  With "select" = 1 the first sufficiently large out-of-place call of a
+// transform times the static table's instance and its alternates ON THE CALLER'S OWN BATCH -- interleaved rounds of
+// back-to-back launches between CUDA events -- and the fastest serves that transform on that device from then on.
+// The call that tunes is synchronous and runs the transform a few dozen times (its output is the same every time).
+struct TuneKey {
+    int mode, e, dir, reorder, tw;
+    bool operator==(const TuneKey& o) const { return mode == o.mode && e == o.e && dir == o.dir && reorder == o.reorder && tw == o.tw; }
+};
+struct TuneRecord {
+    TuneKey key;
+    const KernelEntry* chosen;
+    int ncand;
+    const KernelEntry* cand[4];
+    float ms[4];
+    long long n_points;
+};
+static std::mutex g_tune_mu;
+static std::vector<TuneRecord> g_tuned[kMaxDevices];
+static std::atomic<int> g_opt_select{0};               // 0 static table, 1 first-use selection
+static std::atomic<int> g_opt_select_min_log2{24};     // smallest batch (log2 complex points) worth timing: 2^24 = 128 MiB
+
+static const KernelEntry* tuned_lookup(int dev, const TuneKey& key)
+{
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    for (const TuneRecord& r : g_tuned[dev])
+        if (r.key == key) return r.chosen;
+    return nullptr;
+}
+
+static int autotune(DeviceState* ds, const TuneKey& key, const KernelEntry* base, const void* d_in, void* d_out, long long n_points,
+                    cudaStream_t stream, const KernelEntry** chosen)
+{
+    TuneRecord rec;
+    memset(&rec, 0, sizeof(rec));
+    rec.key = key;
+    rec.n_points = n_points;
+    rec.cand[0] = base;
+    rec.ncand = 1 + find_alternates(key.mode, key.e, key.dir, key.reorder, key.tw, 1, rec.cand + 1, 3);
+    *chosen = base;
+    if (rec.ncand > 1) {
+        const int ROUNDS = 3, BURST = 4;
+        cudaEvent_t ev[4][3][2];
+        bool ok = true;
+        for (int c = 0; c < rec.ncand; c++)
+            for (int r = 0; r < ROUNDS; r++)
+                for (int j = 0; j < 2; j++) ok &= cudaEventCreate(&ev[c][r][j]) == cudaSuccess;
+        int rc = 0;
+        for (int c = 0; c < rec.ncand && !rc; c++) rc = launch_entry(ds, rec.cand[c], d_in, d_out, n_points, stream);  // warm-up: attributes, code, L2
+        for (int r = 0; r < ROUNDS && !rc; r++)
+            for (int c = 0; c < rec.ncand && !rc; c++) {
+                ok &= cudaEventRecord(ev[c][r][0], stream) == cudaSuccess;
+                for (int b = 0; b < BURST && !rc; b++) rc = launch_entry(ds, rec.cand[c], d_in, d_out, n_points, stream);
+                ok &= cudaEventRecord(ev[c][r][1], stream) == cudaSuccess;
+            }
+        ok &= cudaStreamSynchronize(stream) == cudaSuccess;
+        if (!rc && ok) {
+            int best = 0;
+            for (int c = 0; c < rec.ncand; c++) {
+                float t[3] = {0, 0, 0};
+                for (int r = 0; r < ROUNDS; r++) cudaEventElapsedTime(&t[r], ev[c][r][0], ev[c][r][1]);
+                const float lo = fminf(t[0], fminf(t[1], t[2])), hi = fmaxf(t[0], fmaxf(t[1], t[2]));
+                rec.ms[c] = (t[0] + t[1] + t[2] - lo - hi) / BURST;  // median round
+                if (rec.ms[c] < rec.ms[best]) best = c;
+            }
+            // an alternate must win by more than the noise of the protocol to displace the table's instance
+            if (best != 0 && rec.ms[best] > 0.995f * rec.ms[0]) best = 0;
+            *chosen = rec.cand[best];
+        }
+        for (int c = 0; c < rec.ncand; c++)
+            for (int r = 0; r < ROUNDS; r++)
+                for (int j = 0; j < 2; j++) cudaEventDestroy(ev[c][r][j]);
+        if (rc) return rc;
+        if (!ok) return fail_code(SMFFT_ERR_CUDA, "smfft: first-use selection failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    rec.chosen = *chosen;
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    g_tuned[ds->device].push_back(rec);
+    return 0;
+}
+
+// launch one batch on `stream`: n_points complex points = whole transforms of 2^e points each
+static int launch_batch(int mode, int e, int dir, int reorder, int reps, const void* d_in, void* d_out, long long n_points,
+                        cudaStream_t stream)
+{
+    DeviceState* ds = nullptr;
+    if (get_device_state(&ds)) return 1;
+    if (n_points <= 0) return 0;
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail("smfft: device pointers must be 16-byte aligned");
+    const int opt_io = g_opt_io.load(), opt_tw = g_opt_tw.load();
+    int io = reps > 1 ? kernels::IO_LDG
+                      : opt_io == 0 ? -1 : opt_io == 1 ? kernels::IO_LDG : opt_io == 2 ? kernels::IO_TMA
+                      : opt_io == 3 ? kernels::IO_TMA_STG : kernels::IO_REG;
+    const int variant = io == kernels::IO_REG ? (opt_io == 5 ? 2 : 1) : 0;
+    const KernelEntry* k = find_entry(mode, e, dir, reorder, io, opt_tw, reps, variant);
+    if (!k && io == kernels::IO_REG) k = find_entry(mode, e, dir, reorder, -1, opt_tw, reps);  // no register-direct instance: the default one
+    if (!k && io == kernels::IO_TMA_STG) k = find_entry(mode, e, dir, reorder, kernels::IO_TMA, opt_tw, reps);
+    if (k && kernels::io_uses_tma(k->io) && n_points < k->tile_points)  // batch smaller than one tile: thread staging, no tensor map
+        k = find_entry(mode, e, dir, reorder, kernels::IO_LDG, opt_tw, reps);
+    if (!k) return fail("smfft: no kernel instance for mode %d, 2^%d points, dir %d, reorder %d, io %d, tw %d, reps %d", mode, e, dir, reorder, io, opt_tw, reps);
+
+    if (g_opt_select.load() == 1 && opt_io == 0 && reps == 1 && n_points >= (1LL << g_opt_select_min_log2.load())) {
+        const size_t bytes = (size_t)n_points * sizeof(float2);
+        const char *a = (const char*)d_in, *b = (const char*)d_out;
+        const bool overlap = a < b + bytes && b < a + bytes;   // in place: the transform cannot be repeated
+        if (!overlap) {
+            const TuneKey key{mode, e, dir, reorder, opt_tw};
+            const KernelEntry* t = tuned_lookup(ds->device, key);
+            if (!t && autotune(ds, key, k, d_in, d_out, n_points, stream, &t)) return 1;
+            if (t) k = t;
+        }
+    }
+    return launch_entry(ds, k, d_in, d_out, n_points, stream);
 }
 
 struct Call {
@@ -254,7 +375,7 @@ static int timed(double* ms, const Call& c, cudaStream_t stream)
 static int c2c_call(Call* c, const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder, int reps)
 {
     const int e = ilog2_exact(fft_size);
-    if (e < 5 || e > 12) return fail("smfft: wrong FFT length %d (C2C supports 32..4096)", fft_size);
+    if (e < 5 || e > 13 || (e == 13 && reps > 1)) return fail("smfft: wrong FFT length %d (C2C supports 32..8192, FFT_multiple 32..4096)", fft_size);
     if (n_ffts < 0) return fail("smfft: negative nFFTs");
     int dir = inverse ? 1 : 0;
     if (g_opt_quirk4096.load() && fft_size == 4096 && inverse && !reorder) dir = 0;  // CT/SM_FFT_parameters.cuh:388
@@ -293,6 +414,26 @@ int smfft_init(void)
     return get_device_state(&ds);
 }
 
+// what the first-use selection decided on the current device, one line per transform:
+// "mode e dir reorder tw points | chosen io variant threads tile | io/variant:ms ..."; returns the number of bytes written
+int smfft_select_report(char* buf, int cap)
+{
+    if (!buf || cap <= 0) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    int n = 0;
+    buf[0] = 0;
+    for (const TuneRecord& r : g_tuned[dev]) {
+        n += snprintf(buf + n, n < cap ? cap - n : 0, "mode %d e %d dir %d reorder %d tw %d points %lld | chosen io %d variant %d threads %d tile %d |",
+                      r.key.mode, r.key.e, r.key.dir, r.key.reorder, r.key.tw, r.n_points, r.chosen->io, r.chosen->variant, r.chosen->threads, r.chosen->tile_points);
+        for (int c = 0; c < r.ncand && n < cap; c++) n += snprintf(buf + n, cap - n, " %d/%d:%.4f", r.cand[c]->io, r.cand[c]->variant, r.ms[c]);
+        if (n < cap) n += snprintf(buf + n, cap - n, "\n");
+        if (n >= cap) { n = cap - 1; break; }
+    }
+    return n;
+}
+
 const void* smfft_twiddle_table(void)
 {
     DeviceState* ds = nullptr;
@@ -308,7 +449,18 @@ int smfft_set_stream(void* stream)
 int smfft_set_option(const char* key, int value)
 {
     if (!key) return fail("smfft: null option key");
-    if (!strcmp(key, "io")) { if (value < 0 || value > 4) return fail("io must be 0..4"); g_opt_io = value; return 0; }
+    if (!strcmp(key, "io")) { if (value < 0 || value > 5) return fail("io must be 0..5"); g_opt_io = value; return 0; }
+    if (!strcmp(key, "select")) {
+        if (value < 0 || value > 1) return fail("select must be 0 (static table) or 1 (first-use selection)");
+        g_opt_select = value;
+        return 0;
+    }
+    if (!strcmp(key, "select_min_log2_points")) { if (value < 10 || value > 40) return fail("select_min_log2_points must be 10..40"); g_opt_select_min_log2 = value; return 0; }
+    if (!strcmp(key, "select_reset")) {  // forget what has been selected (every device)
+        std::lock_guard<std::mutex> lk(g_tune_mu);
+        for (auto& v : g_tuned) v.clear();
+        return 0;
+    }
     if (!strcmp(key, "twiddle")) { if (value < 0 || value > 1) return fail("twiddle must be 0 or 1"); g_opt_tw = value; return 0; }
     if (!strcmp(key, "quirk_4096")) { g_opt_quirk4096 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
@@ -330,6 +482,8 @@ int smfft_get_option(const char* key)
 {
     if (!key) return -1;
     if (!strcmp(key, "io")) return g_opt_io;
+    if (!strcmp(key, "select")) return g_opt_select;
+    if (!strcmp(key, "select_min_log2_points")) return g_opt_select_min_log2;
     if (!strcmp(key, "twiddle")) return g_opt_tw;
     if (!strcmp(key, "quirk_4096")) return g_opt_quirk4096;
     if (!strcmp(key, "ctas_per_sm")) return g_opt_ctas_per_sm;

@@ -12,10 +12,12 @@ struct KernelEntry {
     int mode, e, dir, reorder, io, tw, reps;  // lookup key (e = log2 of the complex length)
     int tile_points, threads, smem_bytes, minb, stages;
     int ctas;    // CTAs per SM to launch (0 = occupancy limit)
-    int prefer;  // 1 = the measured best staging for this size and mode
+    int prefer;  // 1 = the default instance of this transform (exactly one per key)
+    int tma_best; // 1 = the measured best TMA staging of this transform (= prefer unless a register-direct shape is the default)
     int pf;      // pass after which the next tile is prefetched (-1: top of the iteration)
     int skew;    // small-transform bank de-conflicting on (1) / off (0)
     int dual;    // 1 = two transforms per thread in the packed f32x2 lanes (block_fft_dual.cuh)
+    int variant; // 0 = the instance of the static table; 1, 2 = alternates (candidates of the first-use selection; io = 4 / 5 for the register-direct ones)
     const void* func;
 };
 
@@ -35,8 +37,9 @@ KernelEntry make_entry_shape()
     KernelEntry k;
     k.mode = MODE; k.e = E; k.dir = DIR; k.reorder = REORDER; k.io = IO; k.tw = TW; k.reps = REPS;
     k.tile_points = C::L; k.threads = C::THREADS; k.smem_bytes = kernels::smem_bytes<C, IO, ST, MODE>();
-    k.minb = MINB; k.stages = ST; k.ctas = 0; k.prefer = 0;
+    k.minb = MINB; k.stages = ST; k.ctas = 0; k.prefer = 0; k.tma_best = 0;
     k.pf = PF; k.skew = SKEW; k.dual = DUAL;  // 0 scalar, 1 dual-lane, 2 packed add / subtract
+    k.variant = 0;
     k.func = reinterpret_cast<const void*>(&kernels::smfft_tile_kernel<C, MODE, IO, ST, REPS, MINB, PF>);
     return k;
 }
@@ -51,19 +54,41 @@ KernelEntry make_entry()
     KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS, PF, true, ARITH>();
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
     constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
-    k.prefer = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);
-    if (kernels::RegDirect<E>::ON && kernels::RegDirect<E>::PREFER && MODE == kernels::MODE_C2C && REORDER == 1 && REPS == 1) k.prefer = 0;
+    k.tma_best = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);
+    k.prefer = k.tma_best;
+    if (kernels::RegDirect<E>::ON && kernels::RegDirect<E>::PREFER && MODE == kernels::MODE_C2C && REORDER == 1 && REPS == 1 && TW == TW_LUT) k.prefer = 0;
     return k;
 }
 
-// the register-direct instance (natural-order C2C external): shape from kernels::RegDirect
-template <int E, int DIR, int TW>
+// the register-direct instances (natural-order C2C external): shapes A / B from kernels::RegDirect
+template <int E, int DIR, int TW, int WHICH = 0>
 KernelEntry make_entry_reg()
 {
     using Rd = kernels::RegDirect<E>;
-    KernelEntry k = make_entry_shape<E, Rd::B, Rd::TILE_E, 1, Rd::MINB, kernels::MODE_C2C, DIR, 1, kernels::IO_REG, TW, 1, -1>();
+    constexpr int B = WHICH ? Rd::B_B : Rd::B, TILE_E = WHICH ? Rd::TILE_E_B : Rd::TILE_E, MINB = WHICH ? Rd::MINB_B : Rd::MINB;
+    KernelEntry k = make_entry_shape<E, B, TILE_E, 1, MINB, kernels::MODE_C2C, DIR, 1, kernels::IO_REG, TW, 1, -1>();
     k.ctas = -1;              // one CTA per tile (non-persistent grid)
-    k.prefer = Rd::PREFER;    // 1 = used by default for this size; the TMA instance stays reachable with io = 2
+    k.prefer = WHICH == 0 && Rd::PREFER && TW == TW_LUT;    // 1 = the default for this size (table twiddles); the TMA instances stay reachable with io = 2 / 3
+    k.variant = 1 + WHICH;
+    return k;
+}
+
+// alternates of the TMA path where single launches and the sustained step disagree (tuning.hpp): candidates of the first-use selection
+template <int E, int DIR>
+KernelEntry make_entry_alt_tma()
+{
+    using namespace kernels;
+    static_assert(E == 12 || E == 5, "alternates exist for 4096 points (R = 32 plan) and 32 points (one large CTA per SM)");
+    KernelEntry k;
+    if constexpr (E == 12) {
+        using Tn = TuningR32<12>;  // [32,32,4]: wins single launches, loses under the power cap (profiles/r01_bench_sustained_r32_vs_r16_4096.json)
+        k = make_entry_shape<12, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE_C2C, DIR, 1, IO_TMA, TW_LUT, 1, Tn::PF, true, 0>();
+        k.ctas = Tn::CTAS;
+    } else {
+        k = make_entry_shape<5, 4, 12, 3, 1, MODE_C2C, DIR, 1, IO_TMA, TW_LUT, 1, 1, true, 0>();  // one 32 KB-tile CTA per SM, three stages
+        k.ctas = 1;
+    }
+    k.variant = 1;
     return k;
 }
 
@@ -75,7 +100,7 @@ EntryList build_entries()
     // filled exactly once, by whichever thread gets here first (C++11 guarantees the initialisation of a function-local
     // static is thread-safe); read-only afterwards
     struct Table {
-        KernelEntry tab[112];
+        KernelEntry tab[120];
         int n = 0;
     };
     static const Table table = [] {
@@ -107,6 +132,12 @@ EntryList build_entries()
             tab[i++] = make_entry_reg<E, 0, TW_LUT>(); tab[i++] = make_entry_reg<E, 1, TW_LUT>();
             tab[i++] = make_entry_reg<E, 0, TW_MUFU>(); tab[i++] = make_entry_reg<E, 1, TW_MUFU>();
         }
+        if constexpr (RegDirect<E>::ON_B) {
+            tab[i++] = make_entry_reg<E, 0, TW_LUT, 1>(); tab[i++] = make_entry_reg<E, 1, TW_LUT, 1>();
+        }
+        if constexpr (E == 12 || E == 5) {
+            tab[i++] = make_entry_alt_tma<E, 0>(); tab[i++] = make_entry_alt_tma<E, 1>();
+        }
         // C2C multiple (FFT_multiple_benchmark, 100 reps in place): compute-bound, LDG staging only
         SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_LUT, 100);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 100); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 100);
@@ -131,7 +162,35 @@ EntryList build_entries()
     return EntryList{table.tab, table.n};
 }
 
-// defined one per translation unit (inst_e5.cu ... inst_e12.cu) so the sizes compile in parallel
+// 8192 points: C2C external only (table and MUFU twiddles, TMA and thread staging)
+inline EntryList build_entries_e13()
+{
+    using namespace kernels;
+    struct Table {
+        KernelEntry tab[16];
+        int n = 0;
+    };
+    static const Table table = [] {
+        Table t;
+        KernelEntry* tab = t.tab;
+        int i = 0;
+#define SMFFT_ADD(...) tab[i++] = make_entry<13, __VA_ARGS__>()
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_MUFU, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA, TW_MUFU, 1);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_MUFU, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_MUFU, 1);
+#undef SMFFT_ADD
+        t.n = i;
+        return t;
+    }();
+    return EntryList{table.tab, table.n};
+}
+
+// defined one per translation unit (inst_e5.cu ... inst_e13.cu) so the sizes compile in parallel
 EntryList entries_e5();
 EntryList entries_e6();
 EntryList entries_e7();
@@ -140,6 +199,7 @@ EntryList entries_e9();
 EntryList entries_e10();
 EntryList entries_e11();
 EntryList entries_e12();
+EntryList entries_e13();
 
 }  // namespace host
 }  // namespace smfft

@@ -69,6 +69,15 @@ struct Tuning<12> {
     static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
 };
 
+// 8192 points (beyond the reference's range): one transform still lives in one CTA's shared memory -- a
+// 64 KB tile, two stages, R = 32 ([32,32,8]: 256 threads), one CTA per SM -- so the reference's premise (one FFT never
+// leaves shared memory) holds one size further.  C2C only, both orders, both directions.
+template <>
+struct Tuning<13> {
+    static constexpr int B = 5, TILE_E = 13, F = 1, STAGES = 2, MINB = 1, CTAS = 1, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+
 // Natural-order transforms of 512, 1024 and 4096 points (CT reorder=1, Stockham) run R = 32
 // points per thread: [32,16] / [32,32] needs ONE exchange instead of two -- 39-44 SASS instructions per
 // point instead of 48-52, 48 instead of 64 bytes of shared-memory traffic per point
@@ -145,6 +154,12 @@ struct TuningReal<12> {
 // kernels turn out to be bound by shared-memory wavefronts and latency, not by issue slots alone
 // (profiles/r01_tune_dual_a.csv: equal at 2048 points, 3-12 % slower elsewhere).  It stays as a measured experiment
 // with emulator coverage (tools/tune_dual, tests/test_emu_kernels.py).
+// FFT_multiple of 32 and 64 points (2 and 4 lanes per transform, plan [16, T]): the one exchange goes through warp shuffles
+// (flag 8) -- these kernels run the shared-memory pipe at 81-83 % (profiles/roofline_traffic.json, "multiple"), and the
+// shuffle form moves each value once instead of writing and reading it (A/B: profiles/r02_ab_xshfl_multiple.json)
+#ifndef SMFFT_XSHFL_MULTIPLE
+#define SMFFT_XSHFL_MULTIPLE 1
+#endif
 #if defined(SMFFT_R32_E12)
 constexpr bool kNoR32E12 = false;
 #else
@@ -155,10 +170,10 @@ struct ArithFor {
 #if defined(SMFFT_FORCE_ARITH)
     static constexpr int value = SMFFT_FORCE_ARITH;
 #else
-    static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : 2)
+    static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : (MODE == 0 && (E == 5 || E == 6) && SMFFT_XSHFL_MULTIPLE) ? 10 : 2)
                                  : (MODE == 2 && (E == 11 || E == 12)) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
                                  : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2
-                                 : (MODE == 0 && (E == 11 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans, sustained load
+                                 : (MODE == 0 && (E == 11 || E == 13 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans (and 8192 points), sustained load
 #endif
 };
 
@@ -181,20 +196,50 @@ struct TuningC2R12 {
 // (profiles/r01_tune_register_direct_carveout_default.csv).  PREFER follows the sustained bench step, and there the
 // shape loses even with 16 warps per SM: 1.257 vs 1.303 ms in single launches but 1.40 vs 1.34 ms inside the power-capped step
 // (profiles/r01_register_direct_1024_burst_vs_sustained.json).  The instance stays reachable with io = 4.
+// Round 2: cuFFT's own kernels for 128..1024 points have exactly this structure (profiles/r02_cufft_kernel_shapes.csv:
+// vector_fft<N, EPT<16|32>>, 64..128 threads, 4..12 transforms per CTA, 63..121 registers, one CTA per tile, 4..17 KB of
+// shared memory for the one exchange, large L1) and run 1.23-1.26 ms against 1.29-1.30 ms for the TMA kernels in the same
+// sustained step (profiles/r02_bench_c.json).  Every size from 128 to 1024 points therefore carries up to two
+// register-direct shapes as ALTERNATES: reachable with io = 4 (shape A) / io = 5 (shape B), and candidates of the
+// first-use selection (option "select" = 1, launch.cu), which times them against the default instance on the caller's own
+// batch and keeps the fastest -- the measured regime (burst or sustained, this box's power cap) picks the shape.
 template <int E>
 struct RegDirect {
-    static constexpr bool ON = false, PREFER = false;
+    static constexpr bool ON = false, PREFER = false, ON_B = false;
     static constexpr int B = 4, TILE_E = 10, MINB = 8;
+    static constexpr int B_B = 4, TILE_E_B = 10, MINB_B = 8;
+};
+template <>
+struct RegDirect<7> {  // cuFFT: 16 points per thread, 8 threads per transform, 63 registers
+    static constexpr bool ON = true, PREFER = false, ON_B = true;
+    static constexpr int B = 4, TILE_E = 10, MINB = 16;       // A: 8 transforms per 64-thread CTA, <= 64 registers
+    static constexpr int B_B = 4, TILE_E_B = 11, MINB_B = 6;  // B: 16 transforms per 128-thread CTA
+};
+// 256 points is the one size where the register-direct shape wins in EVERY regime measured (profiles/r02_select_probe_j.json:
+// 1.248-1.258 ms against 1.297 ms for the TMA instance inside the interleaved sustained step, 1.270 vs 1.306 ms in its own
+// consecutive steps, 1.241 vs 1.298 ms in short bursts; cuFFT 1.33-1.36 ms): it is the static default there.
+template <>
+struct RegDirect<8> {  // cuFFT: 16 points per thread, 4 transforms per 64-thread CTA, 80 registers
+    static constexpr bool ON = true, PREFER = true, ON_B = true;
+    static constexpr int B = 4, TILE_E = 10, MINB = 12;
+    static constexpr int B_B = 4, TILE_E_B = 11, MINB_B = 6;
+};
+template <>
+struct RegDirect<9> {  // cuFFT: 32 points per thread, 4 transforms per 64-thread CTA, 121 registers
+    static constexpr bool ON = true, PREFER = false, ON_B = true;
+    static constexpr int B = 5, TILE_E = 11, MINB = 8;
+    static constexpr int B_B = 4, TILE_E_B = 10, MINB_B = 12;
 };
 template <>
 struct RegDirect<10> {
-    static constexpr bool ON = true;
+    static constexpr bool ON = true, ON_B = true;
 #if defined(SMFFT_REGDIRECT_DEFAULT)
     static constexpr bool PREFER = true;
 #else
     static constexpr bool PREFER = false;
 #endif
-    static constexpr int B = 5, TILE_E = 11, MINB = 8;  // 93 registers: eight CTAs = 16 warps per SM (six: 1.263 / 1.42 ms)
+    static constexpr int B = 5, TILE_E = 11, MINB = 8;        // A: 93 registers: eight CTAs = 16 warps per SM (six: 1.263 / 1.42 ms)
+    static constexpr int B_B = 5, TILE_E_B = 12, MINB_B = 4;  // B: cuFFT's shape, 4 transforms per 128-thread CTA
 };
 
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple

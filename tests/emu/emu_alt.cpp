@@ -100,6 +100,42 @@ int emu_run_late(const void* in, void* out, int variant, long long n_ffts, int g
     return -1;
 }
 
+}  // extern "C"
+
+// the product's ALTERNATE instances (tuning.hpp RegDirect shapes A / B, alternate TMA shapes): candidates of the first-use
+// selection.  which: 0 = register-direct A, 1 = register-direct B, 2 = alternate TMA shape (4096 points R = 32, 32 points one large CTA)
+template <int E, int WHICH>
+static int run_reg_alt(const float2* i, float2* o, long long n_ffts, int dir, int grid)
+{
+    using Rd = kernels::RegDirect<E>;
+    constexpr int B = WHICH ? Rd::B_B : Rd::B, TILE_E = WHICH ? Rd::TILE_E_B : Rd::TILE_E;
+    if constexpr (WHICH ? Rd::ON_B : Rd::ON) {
+        if (dir == 0) return run_cfg<E, B, (1 << (TILE_E - E)), 0, 0, 1, kernels::IO_REG, TW_LUT, 1, 1, -1>(i, o, n_ffts, grid, nullptr);
+        return run_cfg<E, B, (1 << (TILE_E - E)), 0, 1, 1, kernels::IO_REG, TW_LUT, 1, 1, -1>(i, o, n_ffts, grid, nullptr);
+    }
+    return -3;
+}
+
+extern "C" {
+
+int emu_run_alternate(const void* in, void* out, int e, int which, long long n_ffts, int dir, int grid)
+{
+    const float2* i = (const float2*)in;
+    float2* o = (float2*)out;
+    if (which == 2) {
+        using T12 = kernels::TuningR32<12>;
+        if (e == 12 && dir == 0) return run_cfg<12, T12::B, 1, 0, 0, 1, kernels::IO_TMA, TW_LUT, T12::STAGES, 1, T12::PF>(i, o, n_ffts, grid, nullptr);
+        if (e == 12 && dir == 1) return run_cfg<12, T12::B, 1, 0, 1, 1, kernels::IO_TMA, TW_LUT, T12::STAGES, 1, T12::PF>(i, o, n_ffts, grid, nullptr);
+        if (e == 5 && dir == 0) return run_cfg<5, 4, 128, 0, 0, 1, kernels::IO_TMA, TW_LUT, 3, 1, 1>(i, o, n_ffts, grid, nullptr);
+        if (e == 5 && dir == 1) return run_cfg<5, 4, 128, 0, 1, 1, kernels::IO_TMA, TW_LUT, 3, 1, 1>(i, o, n_ffts, grid, nullptr);
+        return -3;
+    }
+#define RA(E) if (e == E) return which == 0 ? run_reg_alt<E, 0>(i, o, n_ffts, dir, grid) : run_reg_alt<E, 1>(i, o, n_ffts, dir, grid);
+    RA(7) RA(8) RA(9) RA(10)
+#undef RA
+    return -3;
+}
+
 int emu_alt_length(int variant)
 {
     static const int n[] = {1024, 1024, 512, 128, 4096, 64, 32, 2048};

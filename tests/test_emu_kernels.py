@@ -26,6 +26,7 @@ def emu():
     lib.emu_run.argtypes = [P, P, I, LL, I, I, I, I, I, I, I, D]
     lib.emu_run_alt.argtypes = [P, P, I, LL, I, I, I, I, I, D]
     lib.emu_run_compat.argtypes = [P, P, I, LL, I, I, I, D]
+    lib.emu_run_alternate.argtypes = [P, P, I, I, LL, I, I]
     lib.emu_run_compat_ct.argtypes = [P, P, I, LL, I, I, I, D, ctypes.POINTER(ctypes.c_longlong)]
     lib.emu_run_late.argtypes = [P, P, I, LL, I]
     lib.emu_run_dual.argtypes = [P, P, I, I, LL, I, I, I, I, I, D]
@@ -231,6 +232,20 @@ def test_reference_device_api_engines(emu, e):
             w = O.ct_c2c_fp64(w, bool(direction), bool(reorder))
         assert O.rel_l2(out, w) < TOL
     assert warps >= 1
+
+
+@pytest.mark.parametrize("e,which", [(7, 0), (7, 1), (8, 0), (8, 1), (9, 0), (9, 1), (10, 0), (10, 1), (12, 2), (5, 2)])
+def test_alternate_instances(emu, e, which):
+    """The product's alternates -- register-direct shapes A / B for 128..1024 points (cuFFT-shaped: global -> registers ->
+    passes -> global, one CTA per tile), the R = 32 plan for 4096 points, one large CTA at 32 points -- i.e. every candidate
+    the first-use selection (option "select") may pick: same values as the static table's instances, ragged batch tail."""
+    n = 1 << e
+    nf = 2 * max(1, 8192 // n) + 3
+    x = O.uniform_c64(nf, n, seed=e + which)
+    for direction in (0, 1):
+        out = np.zeros_like(x)
+        assert emu.emu_run_alternate(x.ctypes.data, out.ctypes.data, e, which, nf, direction, 3) == 0, (e, which)
+        assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), True)) < TOL, (e, which, direction)
 
 
 @pytest.mark.parametrize("variant,e,kind", [(0, 12, "c2c_fwd_r"), (1, 12, "c2c_inv_n"), (2, 10, "c2c_fwd_n"), (3, 8, "c2c_fwd_r"),

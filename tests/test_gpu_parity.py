@@ -52,7 +52,7 @@ def run_c2c(sm, x, inverse, reorder):
     return c64(dy)
 
 
-@pytest.mark.parametrize("io", [0, 1, 2, 3, 4])   # auto / thread-staged / TMA in+out / TMA in, registers out / register-direct (1024 natural, else default)
+@pytest.mark.parametrize("io", [0, 1, 2, 3, 4, 5])   # auto / thread-staged / TMA in+out / TMA in, registers out / register-direct shapes A, B (128..1024 natural, else default)
 @pytest.mark.parametrize("tw", [0, 1])
 @pytest.mark.parametrize("n", SIZES)
 def test_c2c_vs_oracle(sm, n, io, tw):
@@ -500,12 +500,13 @@ def test_full_size_properties_4GiB_stockham_and_real(sm):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("n", [64, 128, 512, 2048])
-@pytest.mark.parametrize("io", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize("io", [0, 1, 2, 3, 4, 5])
 def test_in_place_every_staging(sm, n, io):
     """d_output == d_input for the sizes and stagings the first in-place test left out: N = 128 (whose default stores
-    from registers, IO_TMA_STG) and every staging explicitly.  Safe because a tile is completely staged (TMA load or
-    thread copy) before any of its results is written, and tiles do not overlap."""
+    from registers, IO_TMA_STG), N = 256 (whose default is register-direct) and every staging explicitly.  Safe because a
+    tile is completely staged (TMA load, thread copy, or -- register-direct -- every thread's loads consumed by the first pass
+    before the first barrier) before any of its results is written, and tiles do not overlap."""
     sm.set_option("io", io)
     nf = 3 * (8192 // n) + 1
     x = O.uniform_c64(nf, n, seed=n + 17)
@@ -649,3 +650,47 @@ def test_compat_multiple_wrappers_run(compat):
         assert compat.compat_stockham_multiple(big.data_ptr(), out.data_ptr(), n, 400) == 0
         assert compat.compat_r2c_multiple(big.data_ptr(), out.data_ptr(), n, 400) == 0
     torch.cuda.synchronize()
+
+
+def test_first_use_selection(sm):
+    """Option "select" = 1: the first large out-of-place call of a transform times the table's instance against its
+    alternates on the caller's batch and keeps the fastest; results stay correct whichever wins, in-place and small calls
+    are never timed, the report lists every candidate, "select_reset" forgets the decisions."""
+    sm.set_option("select_reset", 1)
+    sm.set_option("select", 1)
+    sm.set_option("select_min_log2_points", 20)
+    try:
+        before = sm.launch_count()
+        for n in (32, 128, 512, 1024, 2048, 4096):
+            nf = (1 << 21) // n
+            x = O.uniform_c64(nf, n, seed=n + 31)
+            dx = to_dev(x)
+            dy = torch.zeros_like(dx)
+            sm.exec_c2c(dx, dy, n, nf, False, True)          # tunes (where alternates exist), then runs
+            torch.cuda.synchronize()
+            got = c64(dy)
+            rows = [0, nf // 2, nf - 1]
+            assert O.rel_l2(got[rows], O.ct_c2c_fp64(x[rows], False, True)) < TOL, n
+            dy.zero_()
+            sm.exec_c2c(dx, dy, n, nf, False, True)          # served by the selected instance
+            torch.cuda.synchronize()
+            assert O.rel_l2(c64(dy)[rows], O.ct_c2c_fp64(x[rows], False, True)) < TOL, n
+        rep = sm.select_report()
+        lines = [ln for ln in rep.splitlines() if ln.strip()]
+        assert len(lines) == 6, rep
+        assert sum(ln.count(":") >= 2 for ln in lines) >= 5, rep          # 32, 128, 512, 1024, 4096 have alternates (2048 has none)
+        assert sm.launch_count() - before > 12 + 5 * 13                   # the timing launches were really made
+        # in place and small batches: no timing
+        n0 = sm.launch_count()
+        d = to_dev(O.uniform_c64((1 << 21) // 256, 256, seed=3))
+        sm.exec_c2c(d, d, 256, (1 << 21) // 256, False, True)
+        small = to_dev(O.uniform_c64(64, 256, seed=4))
+        sm.exec_c2c(small, torch.zeros_like(small), 256, 64, False, True)
+        assert sm.launch_count() - n0 == 2
+        assert "e 8 " not in sm.select_report()
+        sm.set_option("select_reset", 1)
+        assert sm.select_report() == ""
+    finally:
+        sm.set_option("select", 0)
+        sm.set_option("select_min_log2_points", 24)
+        sm.set_option("select_reset", 1)

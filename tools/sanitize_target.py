@@ -34,4 +34,60 @@ x = torch.rand((100 * 4096, 2), device="cuda")
 y = torch.empty_like(x)
 sm.FFT_multiple_benchmark(x, y, 1024, 400, False, True)
 sm.FFT_multiple_benchmark(x, y, 32, 12800, False, False)
+
+# round 2: alternates (register-direct shapes A / B, alternate TMA shapes) incl. the first-use selection, the repeated path
+# with three repetitions, the reference-contract wrapper kernels (warp-shuffle engines) and the native device primitive
+import ctypes
+
+from tests.compat.build_compat import build as build_compat
+
+
+def run(n, nf, inverse, reorder):
+    global bad
+    x = O.uniform_c64(nf, n)
+    dx = torch.from_numpy(x.view(np.float32).reshape(nf, n, 2)).cuda()
+    dy = torch.zeros_like(dx)
+    sm.exec_c2c(dx, dy, n, nf, inverse, reorder)
+    torch.cuda.synchronize()
+    bad += O.rel_l2(dy.cpu().numpy().view(np.complex64).reshape(nf, n), O.ct_c2c_fp64(x, inverse, reorder)) > 1e-5
+
+
+for io in (4, 5):
+    sm.set_option("io", io)
+    for n in (128, 256, 512, 1024):
+        run(n, 3 * (8192 // n) + 5, False, True)
+sm.set_option("io", 0)
+sm.set_option("select", 1)
+sm.set_option("select_min_log2_points", 12)
+for n in (32, 128, 1024, 4096):
+    run(n, 3 * (8192 // n) + 5, False, True)
+sm.set_option("select", 0)
+sm.set_option("select_min_log2_points", 24)
+sm.set_option("select_reset", 1)
+for n in (32, 1024, 4096):
+    nf = 2 * (8192 // n) + 3
+    x = torch.rand((nf, n, 2), device="cuda")
+    y = torch.empty_like(x)
+    sm.exec_repeated(x, y, n, nf, False, True, 0, 3)
+    sm.exec_repeated(x, y, n, nf, False, False, 0, 3)
+lib = ctypes.CDLL(build_compat())
+P, I = ctypes.c_void_p, ctypes.c_int
+lib.compat_ct_external.argtypes = [P, P, I, I, I, I]
+lib.compat_ct_multiple.argtypes = [P, P, I, I, I, I]
+lib.native_fft_launch.argtypes = [P, P, I, I, I, I, P]
+lib.native_convolve_launch.argtypes = [P, P, P, I, I, I, P]
+tw = sm.twiddle_table()
+for n in (32, 64, 128, 256, 512, 1024, 2048, 4096):
+    x = torch.rand((400, n, 2), device="cuda")
+    y = torch.empty_like(x)
+    for inverse in (0, 1):
+        for reorder in (1, 0):
+            assert lib.compat_ct_external(x.data_ptr(), y.data_ptr(), n, 400, inverse, reorder) == 0
+    assert lib.compat_ct_multiple(x.data_ptr(), y.data_ptr(), n, 400, 0, 0) == 0
+    assert lib.compat_ct_multiple(x.data_ptr(), y.data_ptr(), n, 400, 0, 1) == 0
+    assert lib.native_fft_launch(x.data_ptr(), y.data_ptr(), n, 384, 0, 1, tw) == 0
+    if n in (256, 1024, 4096):
+        h = torch.rand((n, 2), device="cuda")
+        assert lib.native_convolve_launch(x.data_ptr(), h.data_ptr(), y.data_ptr(), n, 384, 0, tw) == 0
+torch.cuda.synchronize()
 print("sanitize_target done, mismatches:", int(bad))
