@@ -63,7 +63,7 @@ struct BlockCfg {
     static constexpr int XSHFL = (DUAL_ >> 3) & 1;  // the one exchange of a two-pass plan by warp shuffles (T = 2 or 4 lanes per transform)
     static constexpr int THREADS = (F_ * T) >> DUAL;
     static_assert(DUAL_ >= 0 && DUAL_ < 16 && (!REV || ((E_ % B_ == 3 || E_ % B_ == 2) && VEC128_)), "reversed plans: first radix 8 or 4");
-    static_assert(((DUAL_ >> 3) & 1) == 0 || ((DUAL_ & 5) == 0 && B_ == 4 && (E_ == 5 || E_ == 6)), "shuffle exchange: R = 16, 32 or 64 points, plan [16, T]");
+    static_assert(((DUAL_ >> 3) & 1) == 0 || ((DUAL_ & 5) == 0 && B_ == 4 && (E_ == 5 || E_ == 6)), "shuffle exchange: R = 16, 32 or 64 points, plan [16, T]");  // 64 points: built and measured, not used (tuning.hpp)
     static_assert((DUAL_ & 1) == 0 || (DUAL_ == 1 && F_ % 2 == 0 && E_ - B_ >= 4 && E_ >= 7 && B_ >= 4 && (E_ + B_ - 1) / B_ >= 2 &&
                                  std::is_same<Layout_, LayoutSW128>::value && VEC128_),
                   "dual-lane transforms: an even number of transforms per tile, T >= 16, N >= 128, R >= 16, SW128 tile");
@@ -664,6 +664,9 @@ SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t
             }
         });
         static_for<C::R>([&](auto MI) { v[decltype(MI)::value] = w[decltype(MI)::value]; });
+        // no barrier separates this tile's first read from its final write any more, and with fft_reorder = 0 a lane's
+        // result columns overlap the ROW its neighbour read: order them (all lanes of a transform share a warp)
+        plat::sync_warp();
         run_passes<C, PIDX + 1, XF>(v, s, fbase, t, t, tw, hook);
     } else if constexpr (PIDX + 1 < C::P) {
         plat::sync_block();  // every thread has finished reading the previous state of the tile

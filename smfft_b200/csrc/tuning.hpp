@@ -72,10 +72,17 @@ struct Tuning<12> {
 // 8192 points (beyond the reference's range): one transform still lives in one CTA's shared memory -- a
 // 64 KB tile, two stages, R = 32 ([32,32,8]: 256 threads), one CTA per SM -- so the reference's premise (one FFT never
 // leaves shared memory) holds one size further.  C2C only, both orders, both directions.
+#ifndef SMFFT_T13_STAGES
+#define SMFFT_T13_STAGES 2
+#define SMFFT_T13_MINB 1
+#define SMFFT_T13_CTAS 1
+#define SMFFT_T13_STG 0
+#define SMFFT_T13_B 5
+#endif
 template <>
 struct Tuning<13> {
-    static constexpr int B = 5, TILE_E = 13, F = 1, STAGES = 2, MINB = 1, CTAS = 1, PF = 1;
-    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+    static constexpr int B = SMFFT_T13_B, TILE_E = 13, F = 1, STAGES = SMFFT_T13_STAGES, MINB = SMFFT_T13_MINB, CTAS = SMFFT_T13_CTAS, PF = 1;
+    static constexpr int STG = SMFFT_T13_STG, STG_R2C = 0, STG_C2R = 0;
 };
 
 // Natural-order transforms of 512, 1024 and 4096 points (CT reorder=1, Stockham) run R = 32
@@ -154,9 +161,11 @@ struct TuningReal<12> {
 // kernels turn out to be bound by shared-memory wavefronts and latency, not by issue slots alone
 // (profiles/r01_tune_dual_a.csv: equal at 2048 points, 3-12 % slower elsewhere).  It stays as a measured experiment
 // with emulator coverage (tools/tune_dual, tests/test_emu_kernels.py).
-// FFT_multiple of 32 and 64 points (2 and 4 lanes per transform, plan [16, T]): the one exchange goes through warp shuffles
-// (flag 8) -- these kernels run the shared-memory pipe at 81-83 % (profiles/roofline_traffic.json, "multiple"), and the
-// shuffle form moves each value once instead of writing and reading it (A/B: profiles/r02_ab_xshfl_multiple.json)
+// FFT_multiple of 32 points (2 lanes per transform, plan [16, 2]): the one exchange goes through warp shuffles (flag 8) --
+// these kernels run the shared-memory pipe at 81-83 % (profiles/roofline_traffic.json, "multiple"), and the shuffle form
+// moves each value once instead of writing and reading it.  Interleaved A/B (profiles/r02_ab_xshfl_multiple.json):
+// 32 points 0.571 -> 0.444 ms (-22 %); 64 points (4 lanes: a 4x4 transposition per four registers, 24 SHFL + 128 SEL against
+// 8 STS.128 + 16 LDS.64) +7 % / -1 %: the selects cost what the wavefronts save, so it stays on shared memory.
 #ifndef SMFFT_XSHFL_MULTIPLE
 #define SMFFT_XSHFL_MULTIPLE 1
 #endif
@@ -170,7 +179,7 @@ struct ArithFor {
 #if defined(SMFFT_FORCE_ARITH)
     static constexpr int value = SMFFT_FORCE_ARITH;
 #else
-    static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : (MODE == 0 && (E == 5 || E == 6) && SMFFT_XSHFL_MULTIPLE) ? 10 : 2)
+    static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : (MODE == 0 && E == 5 && SMFFT_XSHFL_MULTIPLE) ? 10 : 2)
                                  : (MODE == 2 && (E == 11 || E == 12)) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
                                  : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2
                                  : (MODE == 0 && (E == 11 || E == 13 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans (and 8192 points), sustained load

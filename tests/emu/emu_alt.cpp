@@ -122,6 +122,16 @@ int emu_run_alternate(const void* in, void* out, int e, int which, long long n_f
 {
     const float2* i = (const float2*)in;
     float2* o = (float2*)out;
+    if (e == 13) {  // 8192 points (Tuning<13>): which = reorder | io << 1 (io: 0 TMA as two 256-row boxes per tile, 1 thread staging)
+        using T13 = kernels::Tuning<13>;
+        constexpr int A13 = kernels::ArithFor<13, 0, 1, 1>::value;
+        const int reorder = which & 1, io = which >> 1;
+#define C13(D, RO, IO) if (dir == D && reorder == RO && io == (IO == kernels::IO_TMA ? 0 : 1)) return run_cfg<13, T13::B, 1, 0, D, RO, IO, TW_LUT, T13::STAGES, 1, (IO == kernels::IO_TMA ? T13::PF : 0), A13>(i, o, n_ffts, grid, nullptr);
+        C13(0, 1, kernels::IO_TMA) C13(0, 0, kernels::IO_TMA) C13(1, 1, kernels::IO_TMA) C13(1, 0, kernels::IO_TMA)
+        C13(0, 1, kernels::IO_LDG) C13(0, 0, kernels::IO_LDG) C13(1, 1, kernels::IO_LDG) C13(1, 0, kernels::IO_LDG)
+#undef C13
+        return -3;
+    }
     if (which == 2) {
         using T12 = kernels::TuningR32<12>;
         if (e == 12 && dir == 0) return run_cfg<12, T12::B, 1, 0, 0, 1, kernels::IO_TMA, TW_LUT, T12::STAGES, 1, T12::PF>(i, o, n_ffts, grid, nullptr);
@@ -130,6 +140,7 @@ int emu_run_alternate(const void* in, void* out, int e, int which, long long n_f
         if (e == 5 && dir == 1) return run_cfg<5, 4, 128, 0, 1, 1, kernels::IO_TMA, TW_LUT, 3, 1, 1>(i, o, n_ffts, grid, nullptr);
         return -3;
     }
+
 #define RA(E) if (e == E) return which == 0 ? run_reg_alt<E, 0>(i, o, n_ffts, dir, grid) : run_reg_alt<E, 1>(i, o, n_ffts, dir, grid);
     RA(7) RA(8) RA(9) RA(10)
 #undef RA

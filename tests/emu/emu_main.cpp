@@ -27,7 +27,13 @@ void run_tma_op(const TmaOp& op)
             }
         }
     }
-    if (op.kind == 0) *op.bar ^= 1ull;  // phase complete
+    if (op.kind == 0) {  // complete_tx: the phase flips when every expected byte has arrived (a tile may come as several boxes)
+        const uint64_t bytes = (uint64_t)m->box_rows * 128;
+        uint64_t pending = *op.bar >> 32;
+        if (pending < bytes) { fprintf(stderr, "emu: TMA load completes more bytes than the mbarrier expects\n"); abort(); }
+        pending -= bytes;
+        *op.bar = (pending << 32) | (((*op.bar) & 1ull) ^ (pending == 0 ? 1ull : 0ull));
+    }
 }
 
 void drain_tma(int owner_only, int kind_only)

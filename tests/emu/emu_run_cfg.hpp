@@ -30,8 +30,9 @@ static int run_cfg(const float2* in, float2* out, long long n_ffts, int grid, do
     kernels::TileArgs args;
     const long long n_points = n_ffts * C::N;
     const long long n_tiles = (n_points + C::L - 1) / C::L;
-    args.in_map = emu::TensorMapEmu{(unsigned char*)in, n_points / 16, C::L / 16};
-    args.out_map = emu::TensorMapEmu{(unsigned char*)out, n_points / 16, C::L / 16};
+    constexpr int BOX = C::L / 16 > 256 ? 256 : C::L / 16;  // as launch.cu: a TMA box holds at most 256 rows
+    args.in_map = emu::TensorMapEmu{(unsigned char*)in, n_points / 16, BOX};
+    args.out_map = emu::TensorMapEmu{(unsigned char*)out, n_points / 16, BOX};
     args.gin = in;
     args.gout = out;
     args.n_tiles = n_tiles;

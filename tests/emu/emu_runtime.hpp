@@ -175,9 +175,9 @@ inline unsigned brev32(unsigned v)
 // ---- TMA / mbarrier emulation ----
 typedef emu::TensorMapEmu TensorMap;
 
-inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }  // bit 0 = parity of the phase in progress
+inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }  // bit 0 = parity of the phase in progress, bits 32.. = bytes still expected
 inline void mbar_fence_init() {}
-inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { *bar += (uint64_t)bytes << 32; }
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return (uint32_t)(*bar & 1u) != parity; }
 inline void mbar_wait(uint64_t* bar, uint32_t parity)
 {

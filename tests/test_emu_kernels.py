@@ -248,6 +248,20 @@ def test_alternate_instances(emu, e, which):
         assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), True)) < TOL, (e, which, direction)
 
 
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_8192_point_c2c(emu, which):
+    """8192 points (beyond the reference's range): one transform per 64 KB tile, R = 32 plan [32,32,8], the tile moved as two
+    256-row TMA boxes; natural order and bit-reversed input, both directions, TMA and thread staging, ragged grid."""
+    n = 8192
+    nf = 5
+    x = O.uniform_c64(nf, n, seed=which)
+    reorder = which & 1
+    for direction in (0, 1):
+        out = np.zeros_like(x)
+        assert emu.emu_run_alternate(x.ctypes.data, out.ctypes.data, 13, which, nf, direction, 2) == 0
+        assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL, (which, direction)
+
+
 @pytest.mark.parametrize("variant,e,kind", [(0, 12, "c2c_fwd_r"), (1, 12, "c2c_inv_n"), (2, 10, "c2c_fwd_n"), (3, 8, "c2c_fwd_r"),
                                             (4, 10, "r2c"), (5, 11, "c2r"),
                                             (6, 10, "c2c_fwd_r"), (7, 9, "c2c_inv_r"), (8, 10, "r2c"), (9, 7, "r2c"),

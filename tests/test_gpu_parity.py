@@ -694,3 +694,29 @@ def test_first_use_selection(sm):
         sm.set_option("select", 0)
         sm.set_option("select_min_log2_points", 24)
         sm.set_option("select_reset", 1)
+
+
+@pytest.mark.parametrize("io", [0, 1, 2])
+@pytest.mark.parametrize("tw", [0, 1])
+def test_c2c_8192_points(sm, io, tw):
+    """8192 points -- one size beyond the reference: one transform per 64 KB shared-memory tile (two 256-row
+    TMA boxes), R = 32 plan [32,32,8].  Both orders, both directions, vs the CPU restatement and FP64; ragged batch; in place."""
+    sm.set_option("io", io)
+    sm.set_option("twiddle", tw)
+    n, nf = 8192, 7
+    x = O.uniform_c64(nf, n, seed=8192 + io)
+    for inverse in (False, True):
+        for reorder in (True, False):
+            y = run_c2c(sm, x, inverse, reorder)
+            assert O.rel_l2(y, O.ct_c2c_fp64(x, inverse, reorder)) < TOL, (io, tw, inverse, reorder)
+            assert O.rel_l2(y, O.c_ct_c2c(x, inverse, reorder)) < TOL
+    d = to_dev(x)
+    sm.exec_c2c(d, d, n, nf, False, True)
+    torch.cuda.synchronize()
+    assert O.rel_l2(c64(d), O.ct_c2c_fp64(x, False, True)) < TOL
+    with pytest.raises(sm.SmfftError):
+        sm.FFT_multiple_benchmark(d, d, n, 200, False, True)      # the repeated benchmark stops at 4096 points
+    with pytest.raises(sm.SmfftError):
+        sm.exec_c2c(d, d, 16384, 1, False, True)
+    sm.set_option("io", 0)
+    sm.set_option("twiddle", 0)
