@@ -262,6 +262,48 @@ def cufft_baseline(x, y, steps=5, warmup=3):
             lib.cufftDestroy(h)
 
 
+def steady_state_per_kernel(x, y, sizes=(128, 256, 512, 1024), count=100, tail=20):
+    """ONE kernel at a time, `count` back-to-back launches from an idle GPU, mean of the last `tail` launches (per-launch CUDA
+    events): each kernel in its OWN thermal steady state, free of what its neighbours in a mixed step draw.  Inside the mixed
+    16-launch step a kernel inherits the clocks its neighbours leave behind: cuFFT's 32 / 64 / 2048 / 4096-point kernels run at
+    4.3-5.8 TB/s and keep its 512 / 1024-point kernels cooler than ours get to be (profiles/r02_burst_timeline_p.json)."""
+    import ctypes
+
+    import torch
+
+    import smfft_b200 as sm
+
+    out = {"how": f"{count} back-to-back launches of one kernel after 0.5 s idle, mean of the last {tail}, CUDA events per launch; natural-order C2C, 4 GiB batch"}
+    try:
+        cu = ctypes.CDLL("libcufft.so.11")
+    except OSError:
+        cu = None
+    xp, yp = ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr())
+    for n in sizes:
+        arms = {"ours": lambda: sm.exec_c2c(x, y, n, BATCH_POINTS // n, False, True)}
+        h = ctypes.c_int(0)
+        if cu is not None and cu.cufftPlan1d(ctypes.byref(h), n, 0x29, BATCH_POINTS // n) == 0:
+            arms["cufft"] = lambda: cu.cufftExecC2C(h, xp, yp, -1)
+        row = {}
+        for name, fn in arms.items():
+            fn()
+            torch.cuda.synchronize()
+            time.sleep(0.5)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(count + 1)]
+            ev[0].record()
+            for i in range(count):
+                fn()
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(count)]
+            row[name] = {"first5_ms": round(sum(ts[:5]) / 5, 4), "steady_ms": round(sum(ts[-tail:]) / tail, 4)}
+        if "cufft" in row:
+            row["ours_vs_cufft_steady"] = round(row["cufft"]["steady_ms"] / row["ours"]["steady_ms"], 4)
+            cu.cufftDestroy(h)
+        out[str(n)] = row
+    return out
+
+
 def device_api_leg(x, y, steps=3):
     """The reference's DEVICE API (the product surface a user kernel calls, README.md:10-20 of the reference) on this
     library vs on the reference itself, same launch shapes, same buffers, same sustained protocol: SMFFT_DIT_external<P> and
@@ -510,6 +552,10 @@ def run_ours(args):
         if not args.no_baselines:
             baselines["cufft_ms"] = cufft_baseline(x, y, args.steps, max(args.warmup, 3))
             baselines["reference_sm100a_ms"] = reference_gpu_baseline(x, y, max(3, args.steps // 2), 2)
+            try:
+                baselines["steady_state_per_kernel"] = steady_state_per_kernel(x, y)
+            except Exception as ex:  # pragma: no cover
+                baselines["steady_state_per_kernel"] = {"error": str(ex)[:200]}
         if not args.no_device_api:
             device_api = device_api_leg(x, y)
     if world > 1:

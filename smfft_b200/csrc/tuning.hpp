@@ -70,10 +70,10 @@ struct Tuning<12> {
 };
 
 // 8192 points (beyond the reference's range): one transform still lives in one CTA's shared memory -- a
-// 64 KB tile, two stages, R = 32 ([32,32,8]: 256 threads), one CTA per SM -- so the reference's premise (one FFT never
+// 64 KB tile, three stages, R = 32 ([32,32,8]: 256 threads), one CTA per SM -- so the reference's premise (one FFT never
 // leaves shared memory) holds one size further.  C2C only, both orders, both directions.
 #ifndef SMFFT_T13_STAGES
-#define SMFFT_T13_STAGES 2
+#define SMFFT_T13_STAGES 3  // three 64 KB buffers: 1.375 / 1.57 ms against 1.59 / 1.78 ms with two (profiles/r02_ab_8192_shapes.json); R = 16 (512 threads, four passes): 1.68 / 1.77 ms
 #define SMFFT_T13_MINB 1
 #define SMFFT_T13_CTAS 1
 #define SMFFT_T13_STG 0
@@ -237,7 +237,7 @@ template <>
 struct RegDirect<9> {  // cuFFT: 32 points per thread, 4 transforms per 64-thread CTA, 121 registers
     static constexpr bool ON = true, PREFER = false, ON_B = true;
     static constexpr int B = 5, TILE_E = 11, MINB = 8;
-    static constexpr int B_B = 4, TILE_E_B = 10, MINB_B = 12;
+    static constexpr int B_B = 5, TILE_E_B = 10, MINB_B = 16;  // B: ONE WARP per CTA (two transforms): block barriers cost nothing, 16 CTAs per SM
 };
 template <>
 struct RegDirect<10> {
@@ -248,7 +248,7 @@ struct RegDirect<10> {
     static constexpr bool PREFER = false;
 #endif
     static constexpr int B = 5, TILE_E = 11, MINB = 8;        // A: 93 registers: eight CTAs = 16 warps per SM (six: 1.263 / 1.42 ms)
-    static constexpr int B_B = 5, TILE_E_B = 12, MINB_B = 4;  // B: cuFFT's shape, 4 transforms per 128-thread CTA
+    static constexpr int B_B = 5, TILE_E_B = 10, MINB_B = 16;  // B: ONE WARP per CTA = one transform (cuFFT's 4-transform / 128-thread shape measured 1.29-1.33 ms)
 };
 
 // shape of one kernel instance: MODE 0 C2C / 1 R2C / 2 C2R (kernels::MODE_*), REPS > 1 = FFT_multiple

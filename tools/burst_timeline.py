@@ -46,11 +46,12 @@ def main(out_path, count):
     y = torch.empty_like(x)
     cu = ctypes.CDLL("libcufft.so.11")
     out = {"lib": os.environ.get("SMFFT_LIB", "product"), "count": count}
-    for n in (1024, 128):
+    for n in (128, 256, 512, 1024, 2048, 4096):
         h = ctypes.c_int(0)
         assert cu.cufftPlan1d(ctypes.byref(h), n, 0x29, PTS // n) == 0
-        arms = {"tma": (0, lambda: sm.exec_c2c(x, y, n, PTS // n, False, True)),
+        arms = {"tma": (2 if n == 256 else 0, lambda: sm.exec_c2c(x, y, n, PTS // n, False, True)),   # 256 points: the default is register-direct, io = 2 is its TMA instance
                 "reg_a": (4, lambda: sm.exec_c2c(x, y, n, PTS // n, False, True)),
+                "reg_b": (5, lambda: sm.exec_c2c(x, y, n, PTS // n, False, True)),
                 "cufft": (0, lambda: cu.cufftExecC2C(h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), -1))}
         for name, (io, fn) in arms.items():
             sm.set_option("io", io)
@@ -58,8 +59,9 @@ def main(out_path, count):
             import time
             time.sleep(0.5)   # start every burst from an idle GPU
             ts, c = timeline(fn, count)
-            out[f"{name}_{n}"] = {"ms": ts, "clocks_end": c}
-            print(name, n, "first5", ts[:5], "mid", ts[count // 2 - 2:count // 2 + 3], "last5", ts[-5:], "| clocks", c, flush=True)
+            steady = round(sum(ts[-20:]) / 20, 4)
+            out[f"{name}_{n}"] = {"ms": ts, "clocks_end": c, "first5_mean": round(sum(ts[:5]) / 5, 4), "steady_last20_mean": steady}
+            print(name, n, "first5", ts[:5], "last5", ts[-5:], "steady", steady, "| clocks", c, flush=True)
         cu.cufftDestroy(h)
     sm.set_option("io", 0)
     json.dump(out, open(out_path, "w"))

@@ -13,6 +13,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "c2c"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 reorder = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 pts = 1 << int(os.environ.get("SMFFT_NCU_LOG2_POINTS", "27"))
+sm.set_option("io", int(os.environ.get("SMFFT_IO", "0")))   # 4 / 5: the register-direct alternates
 x = torch.rand((pts, 2), device="cuda")
 y = torch.empty_like(x)
 for _ in range(4):
