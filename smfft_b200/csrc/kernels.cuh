@@ -18,6 +18,11 @@
 #include "smfft/detail/block_fft.cuh"
 #include "smfft/detail/tma.cuh"
 
+// FFT_multiple, natural order: chain the repetitions in registers (1) or go through the tile every time (0, for A/B)
+#ifndef SMFFT_MULTIPLE_IN_REGISTERS
+#define SMFFT_MULTIPLE_IN_REGISTERS 1
+#endif
+
 namespace smfft {
 namespace kernels {
 
@@ -42,6 +47,19 @@ SMFFT_DEV void tile_transform(float2* s, const float2* tw, Hook&& hook = Hook{})
 {
     if constexpr (REPS == 1) {
         detail::block_fft_tile<C, MODE>(s, tw, hook);
+    } else if constexpr (MODE == MODE_C2C && C::REORDER == 1 && !C::DUAL && SMFFT_MULTIPLE_IN_REGISTERS) {
+        // Natural-order C2C ends every transform with the ownership it started with (v[m] = x[t + m T]), so the repetitions
+        // chain in REGISTERS: the tile is read once and written once, shared memory carries only the exchanges between
+        // passes -- what smfft::BlockFFT::exec (include/smfft/device.cuh) gives a user kernel that applies several
+        // transforms in a row.  (fft_reorder = 0 re-reads the tile bit-reversed every time and keeps the loop below.)
+        float2 v[C::R];
+        const int tid = plat::tid();
+        const int t = tid & (C::T - 1), fbase = (tid >> C::A) << C::E;
+        detail::load_natural<C>(v, s, fbase, t);
+#pragma unroll 1
+        for (int rep = 0; rep < REPS; rep++) detail::run_passes<C, 0, detail::XF_C2C>(v, s, fbase, t, t, tw, detail::NoHook{});
+        if constexpr ((!C::SAME_LAYOUT || !detail::LastExchangeSameAsTile<C>::value) && C::P > 1) plat::sync_block();
+        detail::store_result<C, detail::XF_C2C>(v, s, fbase, t);
     } else {
 #pragma unroll 1
         for (int rep = 0; rep < REPS; rep++) {

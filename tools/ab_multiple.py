@@ -22,7 +22,7 @@ def load(path):
 
 A, B = load(sys.argv[1]), load(sys.argv[2])
 out = {"A": sys.argv[1], "B": sys.argv[2], "protocol": "interleaved A B A B, library-timed CUDA events, median of 15", "ms": {}}
-for n in (32, 64, 128):
+for n in [int(a) for a in sys.argv[4].split(",")] if len(sys.argv) > 4 else (32, 64, 128):
     for reorder in (1, 0):
         ta, tb = [], []
         for i in range(18):
