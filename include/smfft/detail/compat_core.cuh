@@ -39,9 +39,32 @@ SMFFT_DEV void ct_dit(float2* s)
 // The body of the external wrapper kernels (SMFFT_DIT_external<P>, CT:534-551): the tile at gin -> transform -> gout, with
 // `s` (>= tile points) as scratch.  Same launch contract; the staging copies of the reference (4 LDG.64 -> 4 STS, barrier,
 // ..., barrier, 4 LDS -> 4 STG.64) are folded into the transform's own first read and last write.
+// The reference's launch shape (one CTA per tile, CT:586-595) caps the bytes in flight at (resident CTAs) x (tile bytes) per
+// SM, so the larger tiles run at latency x concurrency, not at bandwidth.  There a CTA asks L2 for the tile a CTA launched
+// SMFFT_COMPAT_PREFETCH_BYTES later will read: that CTA's loads then come from L2 instead of DRAM and its lifetime (= the
+// concurrency each byte occupies) shrinks.  No extra DRAM traffic, no semantics.  Measured (profiles/
+// r02_compat_prefetch_probe.json): 4096 points -5 % / -2 %, 256 and 1024 points fft_reorder = 0 -6 % / -3 %, natural-order
+// 1024 points +3 % (off there).  The ONE-WARP tiles (N <= 128) do not react at all -- 2.17 ms with any distance, the
+// reference 2.20 ms: 4.2 million one-warp CTAs are bound by the CTA launch rate (about one CTA per 77 ns and SM), which is
+// why the external wrappers of those sizes sit at 1.01x the reference whatever the transform costs.
+#ifndef SMFFT_COMPAT_PREFETCH_BYTES
+#define SMFFT_COMPAT_PREFETCH_BYTES (8 << 20)
+#endif
+template <int TILE_POINTS>
+SMFFT_DEV void prefetch_later_tile(const float2* __restrict__ gin)
+{
+    if constexpr (SMFFT_COMPAT_PREFETCH_BYTES > 0) {
+        constexpr int TILE_BYTES = TILE_POINTS * 8, AHEAD = SMFFT_COMPAT_PREFETCH_BYTES / TILE_BYTES, LINES = TILE_BYTES / 128;
+        const int t = plat::tid();
+        if (t < LINES && plat::bid() + AHEAD < plat::nblocks())
+            plat::prefetch_l2(reinterpret_cast<const char*>(gin) + (size_t)AHEAD * TILE_BYTES + (size_t)t * 128);
+    }
+}
+
 template <int EXP, int FFTS_PER_TILE, int DIR, int REORDER>
 SMFFT_DEV void ct_dit_external(float2* s, const float2* __restrict__ gin, float2* __restrict__ gout)
 {
+    if constexpr (EXP >= 11 || (EXP >= 8 && !REORDER)) prefetch_later_tile<(FFTS_PER_TILE << EXP)>(gin);
     if constexpr (SMFFT_COMPAT_ENGINE && EXP <= 7) {
         detail::wf::warp_tile_fft_global<EXP, DIR, REORDER>(gin, gout);
     } else if constexpr (SMFFT_COMPAT_ENGINE && !REORDER) {

@@ -39,6 +39,8 @@ SMFFT_DEV float4 lds128(const float2* p) { return *reinterpret_cast<const float4
 SMFFT_DEV void sts128(float2* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 SMFFT_DEV float2 ldg_ro(const float2* p) { return __ldg(p); }
+// pull the 128-byte line at p into L2 (no register, no dependency): used by short-lived CTAs for the tile a LATER CTA will read
+SMFFT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SMFFT_DEV float4 ldg128_stream(const float2* p)
 {
     float4 r;

@@ -160,6 +160,7 @@ inline float4 lds128(const float2* p) { rec(p, 16, 0); return *reinterpret_cast<
 inline void sts128(float2* p, float4 v) { rec(p, 16, 1); *reinterpret_cast<float4*>(p) = v; }
 
 inline float2 ldg_ro(const float2* p) { return *p; }
+inline void prefetch_l2(const void*) {}
 inline float4 ldg128_stream(const float2* p) { float4 r; memcpy(&r, p, 16); return r; }
 inline void stg128_stream(float2* p, float4 v) { memcpy(p, &v, 16); }
 inline float2 ldg64_stream(const float2* p) { return *p; }
