@@ -16,9 +16,9 @@ namespace smfft {
 namespace compat {
 
 // the native block FFT under the reference's thread contract: R = 4 points per thread, linear
-// tile on entry/exit, swizzled exchanges, 8-byte shared accesses only (no alignment demand)
+// tile on entry/exit, swizzled exchanges (LayoutSW4: conflict-free for every pass), 8-byte shared accesses only (no alignment demand)
 template <int EXP, int FFTS_PER_TILE, int DIR, int REORDER>
-using Cfg = detail::BlockCfg<EXP, 2, FFTS_PER_TILE, DIR, REORDER, TW_MUFU, detail::LayoutLinear, detail::LayoutSW128, false>;
+using Cfg = detail::BlockCfg<EXP, 2, FFTS_PER_TILE, DIR, REORDER, TW_MUFU, detail::LayoutLinear, detail::LayoutSW4, false>;
 
 #ifndef SMFFT_COMPAT_ENGINE
 #define SMFFT_COMPAT_ENGINE 1  // 0: the shared-memory Stockham passes everywhere (the round-1 path, kept for A/B)

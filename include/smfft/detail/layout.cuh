@@ -54,6 +54,15 @@ struct LayoutSW128R4 {
     static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 7) & 3) << 2); }
 };
 
+// exchange layout for FOUR points per thread (the reference-contract engines, 64-bit accesses only): the scatter after the
+// first pass writes x = 4j + q and the one after the second x = 16 (j >> 2) + (j & 3) + 4q, so sixteen consecutive lanes
+// cover four rows with the same four columns.  Folding the row's low two bits into BOTH column pairs separates them
+// (low4' = ((a ^ b) << 2 | (q ^ b)) resp. ((a ^ b) | (q ^ b) << 2): a bijection of (a, b)); later scatters and every read
+// cover whole rows, which any row-wise permutation keeps conflict-free.  (SW128 leaves these two scatters 2-way conflicted.)
+struct LayoutSW4 {
+    static SMFFT_HOST_DEV int phys(int x) { return x ^ (((x >> 4) & 3) * 5); }
+};
+
 struct LayoutLinear {
     static SMFFT_HOST_DEV int phys(int x) { return x; }
 };
