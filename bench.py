@@ -389,8 +389,9 @@ def other_modes(x, y, reps=5):
             out["stockham_c2c"][str(n)] = {
                 "forward": row(med(lambda: sm.Stockham_external_benchmark(x, y, n, nf, False)), BATCH_POINTS * 16),
                 "inverse": row(med(lambda: sm.Stockham_external_benchmark(x, y, n, nf, True)), BATCH_POINTS * 16)}
-        out["c2c_8192"] = {("reorder" if r else "noreorder"): row(med(lambda: sm.FFT_external_benchmark(x, y, 8192, BATCH_POINTS // 8192, False, bool(r))), BATCH_POINTS * 16)
-                           for r in (1, 0)}   # one size beyond the reference
+        for nbig in (8192, 16384):   # beyond the reference: one transform per 64 / 128 KB tile
+            out[f"c2c_{nbig}"] = {("reorder" if r else "noreorder"): row(med(lambda: sm.FFT_external_benchmark(x, y, nbig, BATCH_POINTS // nbig, False, bool(r))), BATCH_POINTS * 16)
+                                  for r in (1, 0)}
         real_points = 2 * BATCH_POINTS          # the same 4 GiB read as floats
         for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
             nf = real_points // n

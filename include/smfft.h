@@ -49,7 +49,7 @@ extern "C" {
  * kernels into >48 KB dynamic shared memory.  Idempotent; called lazily by everything else. */
 int smfft_init(void);
 
-/* ---- Cooley-Tukey C2C: N = 32..4096 (the reference's range) and 8192 (one size beyond, external only) -----
+/* ---- Cooley-Tukey C2C: N = 32..4096 (the reference's range) and 8192 / 16384 (beyond it, external only) -----
  * replaces int FFT_external_benchmark(float2*, float2*, int FFT_size, int nFFTs, bool inverse,
  *                                     bool reorder, double* FFT_time)                  CT:583-664
  * reorder=1: natural-order DFT; reorder=0: DFT of the bit-reversed input.
@@ -68,7 +68,7 @@ int smfft_exec_c2c(const void* d_in, void* d_out, int fft_size, long long n_ffts
 int smfft_exec_c2c_stream(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder,
                           void* stream);
 
-/* ---- Stockham C2C: N = 32..8192, natural order ------------------------------------------------
+/* ---- Stockham C2C: N = 32..16384, natural order ------------------------------------------------
  * replaces void FFT_external_benchmark(float2*, float2*, int, int, double*)            ST:306-345
  *          void FFT_multiple_benchmark(float2*, float2*, int, int, double*)            ST:348-384
  * The reference's Stockham C2C directory is inverse-only; `inverse` selects the
@@ -134,7 +134,7 @@ int smfft_get_option(const char* key);
 /* the first-use selection's decisions on the current device as text, one line per transform with every candidate's
  * milliseconds; returns the number of bytes written into buf (NUL-terminated) */
 int smfft_select_report(char* buf, int cap);
-/* device address of the current device's twiddle table W_8192^j = exp(-2 pi i j / 8192), j = 0..8191 (float2, rounded
+/* device address of the current device's twiddle table W_16384^j = exp(-2 pi i j / 16384), j = 0..16383 (float2, rounded
  * from FP64): what smfft::BlockFFT<..., TW_LUT>::fill_twiddles (include/smfft/device.cuh) reads.  NULL on failure. */
 const void* smfft_twiddle_table(void);
 /* CUDA stream (cudaStream_t as void*) used by THIS host thread's launches and event timing; NULL = legacy default */

@@ -14,8 +14,8 @@ namespace smfft {
 
 enum { TW_LUT = 0, TW_MUFU = 1 };
 
-// table length: W_8192^j serves every modulus up to 4096 and the R2C/C2R pair pass of real N = 8192
-constexpr int kTwiddleTableLog2 = 13;
+// table length: W_16384^j serves every C2C modulus up to 16384 and the R2C/C2R pair pass of real N = 8192
+constexpr int kTwiddleTableLog2 = 14;
 constexpr int kTwiddleTableSize = 1 << kTwiddleTableLog2;
 
 namespace detail {

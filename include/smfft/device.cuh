@@ -31,7 +31,7 @@
 //   * `exchange` is shared memory, 16-byte aligned, EXCHANGE_POINTS float2, contents undefined afterwards; the same buffer
 //     may be passed to the next exec() without a barrier in between (each exec synchronises before its first write);
 //   * twiddles: TW_MUFU (default; __sincosf like the reference, nothing to set up) or TW_LUT (pass `tw`, a shared-memory
-//     table of TWIDDLE_POINTS float2 filled once per block by fill_twiddles() from the W_8192 table whose device address
+//     table of TWIDDLE_POINTS float2 filled once per block by fill_twiddles() from the global table whose device address
 //     smfft_twiddle_table() of the C ABI returns; one accurate base twiddle per pass, powers in registers);
 //   * N = 2^LOG2N, 32 <= N <= 4096 (one transform never spans blocks, as in the reference); R = 16, or 32 with LOG2R = 5;
 //     FFTS (transforms per block) a power of two -- use it to give small transforms enough threads per block.
@@ -76,10 +76,10 @@ struct BlockFFT {
         for (int m = 0; m < R; m++) tile[x0 + m * T] = v[m];
     }
 
-    // TW_LUT only: fill the block's twiddle table from the library's global W_8192 table; synchronise before the first exec
-    static __device__ __forceinline__ void fill_twiddles(float2* tw, const float2* __restrict__ w8192)
+    // TW_LUT only: fill the block's twiddle table from the library's global table (smfft_twiddle_table()); synchronise before the first exec
+    static __device__ __forceinline__ void fill_twiddles(float2* tw, const float2* __restrict__ wtable)
     {
-        detail::fill_twiddle_table<Cfg, false, 0>(tw, w8192, threadIdx.x, THREADS);
+        detail::fill_twiddle_table<Cfg, false, 0>(tw, wtable, threadIdx.x, THREADS);
     }
 
     // the transform, registers to registers

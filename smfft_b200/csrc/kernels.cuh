@@ -37,7 +37,7 @@ struct TileArgs {
     float2* gout;
     long long n_tiles;
     long long n_points;       // valid float2 points in the batch (tail tile of IO_LDG)
-    const float2* tw;         // W_8192^j table (forward sign)
+    const float2* tw;         // W_16384^j table (forward sign)
     int l2_hint;              // bit 0: TMA loads evict_first, bit 1: TMA stores evict_first
 };
 

@@ -95,7 +95,7 @@ static int get_device_state(DeviceState** out)
         CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
         if (prop.major < 10)
             return fail_code(SMFFT_ERR_CUDA, "smfft: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
-        // twiddle table W_8192^j, forward sign, rounded from FP64 (twiddle.cuh)
+        // twiddle table W_16384^j, forward sign, rounded from FP64 (twiddle.cuh)
         std::vector<float2> h(kTwiddleTableSize);
         for (int j = 0; j < kTwiddleTableSize; j++) {
             const double a = -2.0 * M_PI * (double)j / (double)kTwiddleTableSize;
@@ -130,6 +130,7 @@ static EntryList entries_of(int e)
         case 11: return entries_e11();
         case 12: return entries_e12();
         case 13: return entries_e13();
+        case 14: return entries_e14();
         default: return EntryList{nullptr, 0};
     }
 }
@@ -375,7 +376,7 @@ static int timed(double* ms, const Call& c, cudaStream_t stream)
 static int c2c_call(Call* c, const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder, int reps)
 {
     const int e = ilog2_exact(fft_size);
-    if (e < 5 || e > 13 || (e == 13 && reps > 1)) return fail("smfft: wrong FFT length %d (C2C supports 32..8192, FFT_multiple 32..4096)", fft_size);
+    if (e < 5 || e > 14 || (e >= 13 && reps > 1)) return fail("smfft: wrong FFT length %d (C2C supports 32..16384, FFT_multiple 32..4096)", fft_size);
     if (n_ffts < 0) return fail("smfft: negative nFFTs");
     int dir = inverse ? 1 : 0;
     if (g_opt_quirk4096.load() && fft_size == 4096 && inverse && !reorder) dir = 0;  // CT/SM_FFT_parameters.cuh:388

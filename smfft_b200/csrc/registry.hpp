@@ -162,8 +162,9 @@ EntryList build_entries()
     return EntryList{table.tab, table.n};
 }
 
-// 8192 points: C2C external only (table and MUFU twiddles, TMA and thread staging)
-inline EntryList build_entries_e13()
+// 8192 / 16384 points: C2C external only (table and MUFU twiddles, TMA and thread staging)
+template <int E>
+EntryList build_entries_large()
 {
     using namespace kernels;
     struct Table {
@@ -174,7 +175,7 @@ inline EntryList build_entries_e13()
         Table t;
         KernelEntry* tab = t.tab;
         int i = 0;
-#define SMFFT_ADD(...) tab[i++] = make_entry<13, __VA_ARGS__>()
+#define SMFFT_ADD(...) tab[i++] = make_entry<E, __VA_ARGS__>()
         SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_LUT, 1);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA, TW_LUT, 1);
         SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_MUFU, 1);
@@ -190,7 +191,7 @@ inline EntryList build_entries_e13()
     return EntryList{table.tab, table.n};
 }
 
-// defined one per translation unit (inst_e5.cu ... inst_e13.cu) so the sizes compile in parallel
+// defined one per translation unit (inst_e5.cu ... inst_e14.cu) so the sizes compile in parallel
 EntryList entries_e5();
 EntryList entries_e6();
 EntryList entries_e7();
@@ -200,6 +201,7 @@ EntryList entries_e10();
 EntryList entries_e11();
 EntryList entries_e12();
 EntryList entries_e13();
+EntryList entries_e14();
 
 }  // namespace host
 }  // namespace smfft

@@ -85,6 +85,15 @@ struct Tuning<13> {
     static constexpr int STG = SMFFT_T13_STG, STG_R2C = 0, STG_C2R = 0;
 };
 
+// 16384 points: the tile is 128 KB, so ONE buffer per CTA and one CTA per SM -- load, transform and store of a tile do not
+// overlap inside the CTA (the price of staying inside one CTA's shared memory: about 60 % of the roofline).  R = 16,
+// [16,16,16,4], 1024 threads (32 warps, 64 registers each).  C2C only.
+template <>
+struct Tuning<14> {
+    static constexpr int B = 4, TILE_E = 14, F = 1, STAGES = 1, MINB = 1, CTAS = 1, PF = -1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
+
 // Natural-order transforms of 512, 1024 and 4096 points (CT reorder=1, Stockham) run R = 32
 // points per thread: [32,16] / [32,32] needs ONE exchange instead of two -- 39-44 SASS instructions per
 // point instead of 48-52, 48 instead of 64 bytes of shared-memory traffic per point
@@ -182,7 +191,7 @@ struct ArithFor {
     static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : (MODE == 0 && E == 5 && SMFFT_XSHFL_MULTIPLE) ? 10 : 2)
                                  : (MODE == 2 && (E == 11 || E == 12)) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
                                  : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2
-                                 : (MODE == 0 && (E == 11 || E == 13 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans (and 8192 points), sustained load
+                                 : (MODE == 0 && (E == 11 || E == 13 || E == 14 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans (and 8192 points), sustained load
 #endif
 };
 

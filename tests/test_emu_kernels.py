@@ -251,17 +251,19 @@ def test_alternate_instances(emu, e, which):
 
 
 @pytest.mark.parametrize("which", [0, 1, 2, 3])
-def test_8192_point_c2c(emu, which):
-    """8192 points (beyond the reference's range): one transform per 64 KB tile, R = 32 plan [32,32,8], the tile moved as two
-    256-row TMA boxes; natural order and bit-reversed input, both directions, TMA and thread staging, ragged grid."""
-    n = 8192
-    nf = 5
+@pytest.mark.parametrize("e", [13, 14])
+def test_8192_and_16384_point_c2c(emu, e, which):
+    """8192 and 16384 points (beyond the reference's range): one transform per 64 / 128 KB tile -- R = 32 plan [32,32,8] with
+    three buffers, R = 16 plan [16,16,16,4] with ONE buffer -- the tile moved as two / four 256-row TMA boxes; natural order
+    and bit-reversed input, both directions, TMA and thread staging, ragged grid."""
+    n = 1 << e
+    nf = 5 if e == 13 else 3
     x = O.uniform_c64(nf, n, seed=which)
     reorder = which & 1
     for direction in (0, 1):
         out = np.zeros_like(x)
-        assert emu.emu_run_alternate(x.ctypes.data, out.ctypes.data, 13, which, nf, direction, 2) == 0
-        assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL, (which, direction)
+        assert emu.emu_run_alternate(x.ctypes.data, out.ctypes.data, e, which, nf, direction, 2) == 0
+        assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), bool(reorder))) < TOL, (e, which, direction)
 
 
 @pytest.mark.parametrize("variant,e,kind", [(0, 12, "c2c_fwd_r"), (1, 12, "c2c_inv_n"), (2, 10, "c2c_fwd_n"), (3, 8, "c2c_fwd_r"),

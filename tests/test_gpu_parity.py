@@ -698,13 +698,15 @@ def test_first_use_selection(sm):
 
 @pytest.mark.parametrize("io", [0, 1, 2])
 @pytest.mark.parametrize("tw", [0, 1])
-def test_c2c_8192_points(sm, io, tw):
-    """8192 points -- one size beyond the reference: one transform per 64 KB shared-memory tile (two 256-row
-    TMA boxes), R = 32 plan [32,32,8].  Both orders, both directions, vs the CPU restatement and FP64; ragged batch; in place."""
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_c2c_beyond_the_reference(sm, n, io, tw):
+    """8192 and 16384 points -- beyond the reference: one transform per 64 / 128 KB shared-memory tile (two /
+    four 256-row TMA boxes), R = 32 plan [32,32,8] / R = 16 plan [16,16,16,4].  Both orders, both directions, vs the CPU
+    restatement and FP64; ragged batch; in place."""
     sm.set_option("io", io)
     sm.set_option("twiddle", tw)
-    n, nf = 8192, 7
-    x = O.uniform_c64(nf, n, seed=8192 + io)
+    nf = 7 if n == 8192 else 5
+    x = O.uniform_c64(nf, n, seed=n + io)
     for inverse in (False, True):
         for reorder in (True, False):
             y = run_c2c(sm, x, inverse, reorder)
@@ -717,6 +719,6 @@ def test_c2c_8192_points(sm, io, tw):
     with pytest.raises(sm.SmfftError):
         sm.FFT_multiple_benchmark(d, d, n, 200, False, True)      # the repeated benchmark stops at 4096 points
     with pytest.raises(sm.SmfftError):
-        sm.exec_c2c(d, d, 16384, 1, False, True)
+        sm.exec_c2c(d, d, 32768, 1, False, True)
     sm.set_option("io", 0)
     sm.set_option("twiddle", 0)
