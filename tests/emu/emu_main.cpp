@@ -199,6 +199,20 @@ int emu_product_flavour(int e, int mode)
     return -1;
 }
 
+// the register-direct alternates of the tuning table: on | prefer << 1 | on_b << 2 | B << 4 | TILE_E << 8 | MINB << 16 (shape A), or shape B with which = 1
+int emu_regdirect_info(int e, int which)
+{
+#define RD(E)                                                                                                                   \
+    if (e == E) {                                                                                                               \
+        using Rd = kernels::RegDirect<E>;                                                                                       \
+        return (Rd::ON ? 1 : 0) | (Rd::PREFER ? 2 : 0) | (Rd::ON_B ? 4 : 0) | ((which ? Rd::B_B : Rd::B) << 4) |               \
+               ((which ? Rd::TILE_E_B : Rd::TILE_E) << 8) | ((which ? Rd::MINB_B : Rd::MINB) << 16);                            \
+    }
+    RD(5) RD(6) RD(7) RD(8) RD(9) RD(10) RD(11) RD(12)
+#undef RD
+    return -1;
+}
+
 int emu_tile_points(int e)
 {
     switch (e) {

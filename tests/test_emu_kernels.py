@@ -405,6 +405,16 @@ def test_product_flavours(emu):
     assert [f(e, C2R)["arith"] for e in range(5, 13)] == [2, 2, 2, 2, 2, 2, 6, 6]
     assert [f(e, C2R)["mirror_c2r"] for e in range(5, 13)] == [0, 0, 0, 0, 0, 0, 1, 1]
     assert f(11, C2R)["B"] == 4 and f(12, C2R)["B"] == 5
+    # register-direct alternates (first-use selection candidates, io = 4 / 5): shapes A and B exist for 128..1024 points only;
+    # 256 points is the one size whose STATIC default is register-direct (it wins in every measured regime)
+    emu.emu_regdirect_info.argtypes = [ctypes.c_int, ctypes.c_int]
+    rd = {e: emu.emu_regdirect_info(e, 0) for e in range(5, 13)}
+    assert [rd[e] & 1 for e in range(5, 13)] == [0, 0, 1, 1, 1, 1, 0, 0]            # ON
+    assert [(rd[e] >> 2) & 1 for e in range(5, 13)] == [0, 0, 1, 1, 1, 1, 0, 0]     # ON_B
+    assert [(rd[e] >> 1) & 1 for e in range(5, 13)] == [0, 0, 0, 1, 0, 0, 0, 0]     # PREFER: 256 points only
+    assert [(rd[e] >> 4) & 15 for e in (7, 8, 9, 10)] == [4, 4, 5, 5]               # points per thread like cuFFT's kernels (16, 16, 32, 32)
+    rdb = {e: emu.emu_regdirect_info(e, 1) for e in (9, 10)}
+    assert all(((v >> 8) & 255) - ((v >> 4) & 15) == 5 for v in rdb.values())       # shape B at 512 / 1024 points: one warp per CTA
     # C2C natural order: R = 32 single-exchange plans at 512 / 1024 points, packed R = 16 at 2048 / 4096 points
     assert [f(e, C2C)["B"] for e in range(5, 13)] == [4, 4, 4, 4, 5, 5, 4, 4]
     assert [f(e, C2C)["arith"] for e in range(5, 13)] == [0, 0, 0, 0, 0, 0, 2, 2]
