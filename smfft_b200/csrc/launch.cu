@@ -270,8 +270,18 @@ static int autotune(DeviceState* ds, const TuneKey& key, const KernelEntry* base
         for (int c = 0; c < rec.ncand; c++)
             for (int r = 0; r < ROUNDS; r++)
                 for (int j = 0; j < 2; j++) ok &= cudaEventCreate(&ev[c][r][j]) == cudaSuccess;
-        int rc = 0;
-        for (int c = 0; c < rec.ncand && !rc; c++) rc = launch_entry(ds, rec.cand[c], d_in, d_out, n_points, stream);  // warm-up: attributes, code, L2
+        int rc = launch_entry(ds, rec.cand[0], d_in, d_out, n_points, stream);  // warm-up: attributes, code, L2
+        for (int c = 1; c < rec.ncand && !rc;) {  // an alternate that cannot be launched here (shared memory, registers) is dropped, not fatal
+            if (launch_entry(ds, rec.cand[c], d_in, d_out, n_points, stream)) {
+                for (int j = c; j + 1 < rec.ncand; j++) rec.cand[j] = rec.cand[j + 1];
+                rec.ncand--;
+                g_err[0] = 0;
+                g_err_code = SMFFT_OK;
+                cudaGetLastError();
+            } else {
+                c++;
+            }
+        }
         for (int r = 0; r < ROUNDS && !rc; r++)
             for (int c = 0; c < rec.ncand && !rc; c++) {
                 ok &= cudaEventRecord(ev[c][r][0], stream) == cudaSuccess;
