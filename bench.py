@@ -512,17 +512,24 @@ def run_ours(args):
         # the ceiling e2e runs against: bare copies of the same pinned buffers, H2D and D2H concurrently on two streams
         # (what the pipeline overlaps), no FFT; every rank at the same time, max over ranks -- the host-side limit at N ranks
         s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-        copy_ms = None
-        for _ in range(4):  # the first pass touches the pinned pages; the best of the rest is the ceiling
+        xf, yf, hxf, hyf = x.view(-1), y.view(-1), hx.view(-1), hy.view(-1)
+
+        def bare_copy(chunk_elems):
             barrier()
             c0 = time.perf_counter()
-            with torch.cuda.stream(s_h2d):
-                y.copy_(hx, non_blocking=True)
-            with torch.cuda.stream(s_d2h):
-                hy.copy_(x, non_blocking=True)
+            for o in range(0, xf.numel(), chunk_elems):
+                with torch.cuda.stream(s_h2d):
+                    yf[o:o + chunk_elems].copy_(hxf[o:o + chunk_elems], non_blocking=True)
+                with torch.cuda.stream(s_d2h):
+                    hyf[o:o + chunk_elems].copy_(xf[o:o + chunk_elems], non_blocking=True)
             torch.cuda.synchronize()
-            t_ms = (time.perf_counter() - c0) * 1e3
-            copy_ms = t_ms if copy_ms is None else min(copy_ms, t_ms)
+            return (time.perf_counter() - c0) * 1e3
+
+        copy_ms = None
+        for chunk in (xf.numel(), (128 << 20) // 4, (32 << 20) // 4):   # whole buffer, 128 MiB and 32 MiB pieces: the ceiling is the best any of them does
+            for _ in range(3):       # the first pass touches the pinned pages
+                t_ms = bare_copy(chunk)
+                copy_ms = t_ms if copy_ms is None else min(copy_ms, t_ms)
         cmax, cunits = reduce_job(torch.tensor([copy_ms], dtype=torch.float64, device="cuda"),
                                   torch.tensor([float(2 * BATCH_POINTS * 8)], dtype=torch.float64, device="cuda"))
         copy_peak = cunits / (cmax * 1e-3) / 1e9
@@ -543,8 +550,9 @@ def run_ours(args):
                "device_event_ms_per_step": dev_ms / e2e_steps,
                "api": "smfft_pipeline_host (pinned host buffers, chunked H2D->FFT->D2H on 3 streams), wall clock incl. allocation",
                "peak": copy_peak, "frac": (units2 / (tmax2 * 1e-3) / 1e9) / copy_peak,
-               "peak_how": "bare cudaMemcpyAsync of the same pinned 4 GiB buffers, H2D and D2H concurrently on two streams, all ranks at once, "
-                           "bytes in + bytes out over the max-over-ranks wall time (GB/s, same unit as value)"}
+               "peak_how": "bare cudaMemcpyAsync of the same pinned 4 GiB buffers, H2D and D2H concurrently on two streams (whole buffer, 128 MiB and "
+                           "32 MiB pieces; best of 9), all ranks at once, bytes in + bytes out over the max-over-ranks wall time (GB/s, same unit as "
+                           "value); both numbers are bound by the same PCIe / host path, so frac sits near 1 with a few percent of run-to-run spread"}
         sm.pipeline_release()  # the pipeline's device buffers (6 x 128 MiB) are not needed by the legs that follow
         del hx, hy
 
