@@ -368,13 +368,15 @@ struct PlanDit<6> {
     }
 };
 template <>
-struct PlanDit<5> {  // [4,4,2]; the second transposition brings (Q4, transform bit Q5) into the registers
+struct PlanDit<5> {  // [4,4,2]; the last bit comes in by a one-bit swap (4 SHFL + 12 SEL).  A second 4x4 transposition (6 SHFL + 32 SEL)
+                     // would also bring a transform bit into the registers and make the final store conflict-free, but these one-warp
+                     // engines are issue-bound (ncu: 74 % issue): 2 extra store wavefronts are cheaper than 22 more instructions
     static constexpr int E = 5, NOPS = 5;
     static constexpr bool DIT = true;
     static SMFFT_CX SlotMap init() { return SlotMap{{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11}}; }
     static SMFFT_CX Op op(int i)
     {
-        constexpr Op t[NOPS] = {{OP_S4, 0, 0}, {OP_X4, 0, 1}, {OP_S4, 0, 0}, {OP_X4, 2, 3}, {OP_S2, 0, 0}};
+        constexpr Op t[NOPS] = {{OP_S4, 0, 0}, {OP_X4, 0, 1}, {OP_S4, 0, 0}, {OP_X2, 0, 2}, {OP_S2, 0, 0}};
         return t[i];
     }
 };

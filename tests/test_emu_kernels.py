@@ -210,13 +210,13 @@ def test_reference_device_api_engines(emu, e):
             assert emu.emu_run_compat_ct(x.ctypes.data, out.ctypes.data, e, nf, direction, reorder, reps, ctypes.byref(bank), ctypes.byref(sh)) == 0
             assert O.rel_l2(out, want) < TOL, (e, direction, reorder, reps)
             if not reorder and reps == 1:
-                # fft_reorder = 0: every access conflict-free except the final LINEAR store of 2048 / 4096 points (2 / 4 wavefronts)
-                assert bank.value <= {11: 1.17, 12: 1.51}.get(e, 1.0) + 1e-9, (e, bank.value)
+                # fft_reorder = 0: every access conflict-free except the final LINEAR store of 32 (2), 2048 (2) and 4096 points (4 wavefronts)
+                assert bank.value <= {5: 1.25, 11: 1.17, 12: 1.51}.get(e, 1.0) + 1e-9, (e, bank.value)
             if reorder and e >= 8:
                 assert bank.value <= 1.0 + 1e-9        # natural order above 128 points: Stockham passes, LayoutSW4 exchanges, no conflict anywhere
             if e <= 7:
                 assert bank.value <= 1.25 + 1e-9       # natural order: the bit-reversed store of 32 / 128 points pays 2 wavefronts
-                assert sh.value == {5: 12, 6: 12, 7: 16}[e]  # float shuffles per thread: 6 per 4x4 transposition, 4 per bit swap
+                assert sh.value == ({5: 12, 6: 12, 7: 16}[e] if reorder else {5: 10, 6: 12, 7: 16}[e])  # float shuffles per thread: 6 per 4x4 transposition, 4 per bit swap
         if not reorder:
             # a tile that is only 8-byte aligned takes the 64-bit first read (rotated rows): same values, still conflict-free
             emu.emu_set_compat_misalign(1)
@@ -225,7 +225,7 @@ def test_reference_device_api_engines(emu, e):
             assert emu.emu_run_compat_ct(x.ctypes.data, out.ctypes.data, e, nf, direction, reorder, 1, ctypes.byref(bank), None) == 0
             emu.emu_set_compat_misalign(0)
             assert O.rel_l2(out, want) < TOL
-            assert bank.value <= {11: 1.17, 12: 1.51}.get(e, 1.0) + 1e-9, (e, bank.value)
+            assert bank.value <= {5: 1.25, 11: 1.17, 12: 1.51}.get(e, 1.0) + 1e-9, (e, bank.value)
         xs = (x / np.float32(n)).astype(np.complex64)
         out = np.zeros_like(xs)
         assert emu.emu_run_compat_ct(xs.ctypes.data, out.ctypes.data, e, nf, direction, reorder, 3, None, None) == 0
