@@ -276,7 +276,13 @@ struct ShapeFor {
 #endif
                                                  (MODE != 0 && REPS > 1 && (E == 9 || E == 10)));
     static constexpr bool REAL = MODE != 0 && REPS == 1;
+#if defined(SMFFT_R2C11_R32)
+    // experiment: R2C of 4096 reals on the mirrored R = 32 plan [32,32,2] (12 warps per SM).  Measured (profiles/r02_ab_r2c4096_r32.json):
+    // 1.37 ms in the first launches after idle, but 1.63 vs 1.49 ms interleaved and 1.60 vs 1.53 ms in its own steady state -- not used.
+    static constexpr bool M12 = MODE == 1 && REPS == 1 && (E == 12 || E == 11);
+#else
     static constexpr bool M12 = MODE == 1 && REPS == 1 && E == 12;
+#endif
     static constexpr bool C12 = MODE == 2 && REPS == 1 && E == 12;
     using type = typename std::conditional<M12, TuningR2C12, typename std::conditional<C12, TuningC2R12,
                  typename std::conditional<REAL, TuningReal<E>, typename std::conditional<R32, TuningR32<E>, Tuning<E>>::type>::type>::type>::type;
