@@ -146,10 +146,20 @@ struct TuningReal<10> {
     static constexpr int B = 5, TILE_E = 11, F = 1 << (TILE_E - 10), STAGES = 2, MINB = 4, CTAS = 4, PF = 1;
     static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 1;
 };
+// experiment switches (variant builds): shape of the 4096-real kernels.  One buffer and 8 or 10 CTAs per SM (32 / 40 warps, the CTAs
+// interleave instead of each pipelining two tiles) against the product's two buffers x 6 CTAs: R2C -1..-3 %, C2R +3..+4 %
+// (profiles/r02_ab_real4096_single_stage.json) -- inside the box-to-box spread, the product shape stays.
+#ifndef SMFFT_TR11_STAGES
+#define SMFFT_TR11_STAGES 2
+#define SMFFT_TR11_MINB 6
+#define SMFFT_TR11_CTAS 6
+#define SMFFT_TR11_PF 1
+#define SMFFT_TR11_STG_R2C 1
+#endif
 template <>
 struct TuningReal<11> {
-    static constexpr int B = 4, TILE_E = 11, F = 1, STAGES = 2, MINB = 6, CTAS = 6, PF = 1;
-    static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;  // mirrored R2C: the descending half of the result leaves from registers
+    static constexpr int B = 4, TILE_E = 11, F = 1, STAGES = SMFFT_TR11_STAGES, MINB = SMFFT_TR11_MINB, CTAS = SMFFT_TR11_CTAS, PF = SMFFT_TR11_PF;
+    static constexpr int STG = 0, STG_R2C = SMFFT_TR11_STG_R2C, STG_C2R = 0;  // mirrored R2C: the descending half of the result leaves from registers
 };
 template <>
 struct TuningReal<12> {
