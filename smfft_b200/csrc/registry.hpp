@@ -73,6 +73,17 @@ KernelEntry make_entry_reg()
     return k;
 }
 
+// register-direct R2C (real length 2^(E+1)): shape A of kernels::RegDirect, table twiddles -- an alternate (io = 4, first-use selection)
+template <int E>
+KernelEntry make_entry_reg_r2c()
+{
+    using Rd = kernels::RegDirect<E>;
+    KernelEntry k = make_entry_shape<E, Rd::B, Rd::TILE_E, 1, Rd::MINB, kernels::MODE_R2C, 0, 1, kernels::IO_REG, TW_LUT, 1, -1>();
+    k.ctas = -1;
+    k.variant = 1;
+    return k;
+}
+
 // alternates of the TMA path where single launches and the sustained step disagree (tuning.hpp): candidates of the first-use selection
 template <int E, int DIR>
 KernelEntry make_entry_alt_tma()
@@ -100,7 +111,7 @@ EntryList build_entries()
     // filled exactly once, by whichever thread gets here first (C++11 guarantees the initialisation of a function-local
     // static is thread-safe); read-only afterwards
     struct Table {
-        KernelEntry tab[120];
+        KernelEntry tab[124];
         int n = 0;
     };
     static const Table table = [] {
@@ -136,6 +147,7 @@ EntryList build_entries()
             tab[i++] = make_entry_reg<E, 0, TW_LUT>(); tab[i++] = make_entry_reg<E, 1, TW_LUT>();
             tab[i++] = make_entry_reg<E, 0, TW_MUFU>(); tab[i++] = make_entry_reg<E, 1, TW_MUFU>();
         }
+        if constexpr (RegDirect<E>::ON) tab[i++] = make_entry_reg_r2c<E>();
         if constexpr (RegDirect<E>::ON_B) {
             tab[i++] = make_entry_reg<E, 0, TW_LUT, 1>(); tab[i++] = make_entry_reg<E, 1, TW_LUT, 1>();
         }
