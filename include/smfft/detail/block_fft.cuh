@@ -372,20 +372,41 @@ SMFFT_DEV void fft_pass_scatter(const float2 (&v)[C::R], float2* s, int fbase, i
 
 struct NoHook {
     static constexpr int PASS = 0;
+    static constexpr bool TAIL = false;
     SMFFT_DEV void operator()() const {}
+    SMFFT_DEV void tail() const {}
 };
 // a callable to run once per tile, right after the first barrier that follows pass PASS (clamped to
 // the last exchange of the plan): the kernels use it to time the refill of the previous tile buffer
 template <int PASS_, class F>
 struct HookAt {
     static constexpr int PASS = PASS_;
+    static constexpr bool TAIL = false;
     F f;
     SMFFT_DEV void operator()() const { f(); }
+    SMFFT_DEV void tail() const {}
 };
 template <int PASS_, class F>
 SMFFT_DEV HookAt<PASS_, F> hook_at(F f)
 {
     return HookAt<PASS_, F>{f};
+}
+// a TAIL callable: every thread runs it once per tile right after ITS last read of the tile buffer (the operands of the
+// last pass, i.e. the final exchange); the results leave from registers.  Behind a block barrier inside the callable the
+// buffer is dead, so a TMA load into the very buffer the transform ran in may start there (single-buffer kernels: 16384
+// points, where two 128 KB tiles do not fit one SM) -- the callable also owns the generic -> async proxy fence that needs.
+template <class G>
+struct HookTail {
+    static constexpr int PASS = -2;  // no regular hook
+    static constexpr bool TAIL = true;
+    G g;
+    SMFFT_DEV void operator()() const {}
+    SMFFT_DEV void tail() const { g(); }
+};
+template <class G>
+SMFFT_DEV HookTail<G> hook_tail(G g)
+{
+    return HookTail<G>{g};
 }
 
 // layout of the exchange that follows pass PIDX
@@ -683,6 +704,7 @@ SMFFT_DEV void run_passes(float2 (&v)[C::R], float2* s, int fbase, int vt, int t
                 fft_pass_scatter<C, PIDX, XL>(v, s, fbase, vt);
             plat::sync_block();
             load_natural<C, XL>(v, s, fbase, t);
+            if constexpr (std::remove_reference<Hook>::type::TAIL && PIDX + 1 == C::P - 1) hook.tail();  // this thread's last read of the tile buffer is done
         }
         run_passes<C, PIDX + 1, XF>(v, s, fbase, t, t, tw, hook);
     }

@@ -215,20 +215,38 @@ SMFFT_DEV void tile_kernel_body(const TileArgs& args, unsigned char* smem)
         } else {
             // results leave from registers: a tile buffer is free as soon as every thread has passed
             // the first barrier of the NEXT tile; the refill is issued there or after a later pass (PF)
-            static_assert(IO != IO_TMA_STG || STAGES >= 2, "register-output staging needs two tile buffers");
-            for (long long k = 0; k < my_tiles; k++) {
-                plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
-                const long long p0 = (first + k * step) * C::L;
-                auto refill = [&]() {
-                    const long long kn = k + STAGES - 1;
-                    if (tid == 0 && kn < my_tiles) issue_load(kn);
-                };
-                tile_transform_to_global<C, MODE, REPS>(stage_ptr(k), stw, args.gout + p0, args.n_points - p0,
-                                                        detail::hook_at<(PF < 0 ? 0 : PF)>(refill));
-                // this buffer was written through the generic proxy (exchanges, real-pass scratch) and is refilled by a
-                // TMA load (async proxy) behind the first barrier of the next tile: order the two, as the PTX memory
-                // model asks (the IO_TMA path fences before its store for the same reason)
-                plat::fence_proxy_async();
+            if constexpr (STAGES == 1) {
+                // ONE tile buffer (16384 points: 128 KB): the refill of the SAME buffer is issued as soon as the final exchange
+                // has been read (hook_tail), so the next tile's load runs under the last pass and the stores from registers.
+                // (Parking the lower half of the next tile in a spare 64 KB buffer earlier still changes nothing: the kernel
+                // no longer waits for loads, profiles/r02_ab_16384_single_buffer.json.)
+                static_assert(REPS == 1 && MODE == MODE_C2C && !C::DUAL, "single-buffer overlap: C2C external");
+                if (tid == 0 && my_tiles > 0) issue_load(0);
+                for (long long k = 0; k < my_tiles; k++) {
+                    plat::mbar_wait(&full[0], (uint32_t)(k & 1));
+                    const long long p0 = (first + k * step) * C::L;
+                    auto refill = [&]() {
+                        plat::fence_proxy_async();  // the exchanges wrote the buffer through the generic proxy
+                        plat::sync_block();         // every thread holds its operands of the last pass in registers
+                        if (tid == 0 && k + 1 < my_tiles) issue_load(k + 1);
+                    };
+                    tile_transform_to_global<C, MODE, REPS>(stage_ptr(0), stw, args.gout + p0, args.n_points - p0, detail::hook_tail(refill));
+                }
+            } else {
+                for (long long k = 0; k < my_tiles; k++) {
+                    plat::mbar_wait(&full[k % STAGES], (uint32_t)((k / STAGES) & 1));
+                    const long long p0 = (first + k * step) * C::L;
+                    auto refill = [&]() {
+                        const long long kn = k + STAGES - 1;
+                        if (tid == 0 && kn < my_tiles) issue_load(kn);
+                    };
+                    tile_transform_to_global<C, MODE, REPS>(stage_ptr(k), stw, args.gout + p0, args.n_points - p0,
+                                                            detail::hook_at<(PF < 0 ? 0 : PF)>(refill));
+                    // this buffer was written through the generic proxy (exchanges, real-pass scratch) and is refilled by a
+                    // TMA load (async proxy) behind the first barrier of the next tile: order the two, as the PTX memory
+                    // model asks (the IO_TMA path fences before its store for the same reason)
+                    plat::fence_proxy_async();
+                }
             }
         }
     } else if constexpr (IO == IO_REG) {

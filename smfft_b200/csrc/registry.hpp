@@ -53,7 +53,7 @@ KernelEntry make_entry()
     constexpr int ARITH = kernels::ArithFor<E, MODE, REORDER, REPS>::value;
     KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS, PF, true, ARITH>();
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
-    constexpr bool stg = Tn::STAGES >= 2 && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
+    constexpr bool stg = (Tn::STAGES >= 2 || E == 14) && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
     k.tma_best = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);
     k.prefer = k.tma_best;
     if (kernels::RegDirect<E>::ON && kernels::RegDirect<E>::PREFER && MODE == kernels::MODE_C2C && REORDER == 1 && REPS == 1 && TW == TW_LUT) k.prefer = 0;
@@ -184,7 +184,7 @@ EntryList build_entries_large()
 {
     using namespace kernels;
     struct Table {
-        KernelEntry tab[16];
+        KernelEntry tab[24];
         int n = 0;
     };
     static const Table table = [] {
@@ -192,6 +192,13 @@ EntryList build_entries_large()
         KernelEntry* tab = t.tab;
         int i = 0;
 #define SMFFT_ADD(...) tab[i++] = make_entry<E, __VA_ARGS__>()
+        // 16384 points, one 128 KB buffer: TMA in, results out from registers, the refill issued behind the final exchange
+        if constexpr (Tuning<E>::STAGES == 1) {
+            SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_LUT, 1);
+            SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_LUT, 1);
+            SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_MUFU, 1);
+            SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_MUFU, 1);
+        }
         SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_LUT, 1);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA, TW_LUT, 1);
         SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA, TW_MUFU, 1);

@@ -85,13 +85,26 @@ struct Tuning<13> {
     static constexpr int STG = SMFFT_T13_STG, STG_R2C = 0, STG_C2R = 0;
 };
 
-// 16384 points: the tile is 128 KB, so ONE buffer per CTA and one CTA per SM -- load, transform and store of a tile do not
-// overlap inside the CTA (the price of staying inside one CTA's shared memory: about 60 % of the roofline).  R = 16,
-// [16,16,16,4], 1024 threads (32 warps, 64 registers each).  C2C only.
+// 16384 points: the tile is 128 KB, so ONE buffer per CTA and one CTA per SM.  R = 32, [32,32,16]: 512 threads (16 warps,
+// 112 registers), two exchanges.  The results leave from registers (IO_TMA_STG) and the refill of the one buffer is
+// issued behind the final exchange, so the next tile's load overlaps the last pass and the stores: 2.43 / 2.36 ms (R = 16,
+// [16,16,16,4], TMA store, load -> transform -> store in sequence) -> 1.99 / 1.91 ms (same plan, registers out) -> 1.76 / 1.78 ms
+// (R = 32), natural / bit-reversed input, 4 GiB batches (profiles/r02_ab_16384_single_buffer.json).  What is left is not a
+// wait for memory (ncu: no long-scoreboard stalls) but 16 warps alone on an SM between block barriers (issue slots 43 %
+// busy): 0.74 of the roofline is the price of keeping one transform inside one CTA's shared memory.  C2C only.
+#ifndef SMFFT_T14_STG
+#define SMFFT_T14_STG 1
+#endif
+#ifndef SMFFT_T14_B
+#define SMFFT_T14_B 5  // reversed [4,16,16,16]: 2.14 / 2.05 ms; scalar arithmetic or MUFU twiddles: slower in one order or the other
+#endif
+#ifndef SMFFT_T14_ARITH
+#define SMFFT_T14_ARITH 2
+#endif
 template <>
 struct Tuning<14> {
-    static constexpr int B = 4, TILE_E = 14, F = 1, STAGES = 1, MINB = 1, CTAS = 1, PF = -1;
-    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+    static constexpr int B = SMFFT_T14_B, TILE_E = 14, F = 1, STAGES = 1, MINB = 1, CTAS = 1, PF = -1;
+    static constexpr int STG = SMFFT_T14_STG, STG_R2C = 0, STG_C2R = 0;
 };
 
 // Natural-order transforms of 512, 1024 and 4096 points (CT reorder=1, Stockham) run R = 32
@@ -201,7 +214,8 @@ struct ArithFor {
     static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : (MODE == 0 && E == 5 && SMFFT_XSHFL_MULTIPLE) ? 10 : 2)
                                  : (MODE == 2 && (E == 11 || E == 12)) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
                                  : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2
-                                 : (MODE == 0 && (E == 11 || E == 13 || E == 14 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans (and 8192 points), sustained load
+                                 : (MODE == 0 && E == 14) ? SMFFT_T14_ARITH
+                                 : (MODE == 0 && (E == 11 || E == 13 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans (and 8192 points), sustained load
 #endif
 };
 

@@ -132,13 +132,15 @@ int emu_run_alternate(const void* in, void* out, int e, int which, long long n_f
 #undef C13
         return -3;
     }
-    if (e == 14) {  // 16384 points (Tuning<14>): one 128 KB buffer, four TMA boxes per tile, [16,16,16,4]; which as for 8192
+    if (e == 14) {  // 16384 points (Tuning<14>): one 128 KB buffer, four TMA boxes per tile, [16,16,16,4]; which as for 8192, io 2 = TMA in / registers out
         using T14 = kernels::Tuning<14>;
         constexpr int A14 = kernels::ArithFor<14, 0, 1, 1>::value;
         const int reorder = which & 1, io = which >> 1;
-#define C14(D, RO, IO) if (dir == D && reorder == RO && io == (IO == kernels::IO_TMA ? 0 : 1)) return run_cfg<14, T14::B, 1, 0, D, RO, IO, TW_LUT, T14::STAGES, 1, (IO == kernels::IO_TMA ? T14::PF : 0), A14>(i, o, n_ffts, grid, nullptr);
+#define C14(D, RO, IO) if (dir == D && reorder == RO && io == (IO == kernels::IO_TMA ? 0 : IO == kernels::IO_LDG ? 1 : 2)) return run_cfg<14, T14::B, 1, 0, D, RO, IO, TW_LUT, T14::STAGES, 1, (IO == kernels::IO_TMA ? T14::PF : 0), A14>(i, o, n_ffts, grid, nullptr);
         C14(0, 1, kernels::IO_TMA) C14(0, 0, kernels::IO_TMA) C14(1, 1, kernels::IO_TMA) C14(1, 0, kernels::IO_TMA)
         C14(0, 1, kernels::IO_LDG) C14(0, 0, kernels::IO_LDG) C14(1, 1, kernels::IO_LDG) C14(1, 0, kernels::IO_LDG)
+        // io = 2: TMA in, registers out, the SAME buffer refilled behind the final exchange (hook_tail)
+        C14(0, 1, kernels::IO_TMA_STG) C14(0, 0, kernels::IO_TMA_STG) C14(1, 1, kernels::IO_TMA_STG) C14(1, 0, kernels::IO_TMA_STG)
 #undef C14
         return -3;
     }

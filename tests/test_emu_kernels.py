@@ -250,12 +250,12 @@ def test_alternate_instances(emu, e, which):
         assert O.rel_l2(out, O.ct_c2c_fp64(x, bool(direction), True)) < TOL, (e, which, direction)
 
 
-@pytest.mark.parametrize("which", [0, 1, 2, 3])
-@pytest.mark.parametrize("e", [13, 14])
+@pytest.mark.parametrize("e,which", [(13, 0), (13, 1), (13, 2), (13, 3), (14, 0), (14, 1), (14, 2), (14, 3), (14, 4), (14, 5)])
 def test_8192_and_16384_point_c2c(emu, e, which):
     """8192 and 16384 points (beyond the reference's range): one transform per 64 / 128 KB tile -- R = 32 plan [32,32,8] with
     three buffers, R = 16 plan [16,16,16,4] with ONE buffer -- the tile moved as two / four 256-row TMA boxes; natural order
-    and bit-reversed input, both directions, TMA and thread staging, ragged grid."""
+    and bit-reversed input, both directions, TMA and thread staging, ragged grid; 16384 points also with the results
+    leaving from registers while the one buffer is refilled behind the final exchange (which = 4, 5)."""
     n = 1 << e
     nf = 5 if e == 13 else 3
     x = O.uniform_c64(nf, n, seed=which)

@@ -69,6 +69,26 @@ def test_c2c_vs_oracle(sm, n, io, tw):
     sm.set_option("twiddle", 0)
 
 
+@pytest.mark.parametrize("io", [0, 2, 3])
+def test_16384_points_many_tiles_per_cta(sm, io):
+    """16384 points with more tiles than SMs, so every persistent CTA refills its ONE 128 KB buffer: through the TMA store
+    path (io = 2) and with the results leaving from registers while the same buffer is refilled behind the final exchange
+    (io = 3).  Both orders and directions vs FP64; the two stagings agree bit for bit."""
+    n, nf = 16384, 2 * 148 + 37
+    x = O.uniform_c64(nf, n, seed=77 + io)
+    sm.set_option("io", io)
+    try:
+        for inverse, reorder in ((False, True), (True, False), (False, False)):
+            y = run_c2c(sm, x, inverse, reorder)
+            assert O.rel_l2(y, O.ct_c2c_fp64(x, inverse, reorder)) < TOL, (io, inverse, reorder)
+            if io:
+                sm.set_option("io", 5 - io)
+                assert np.array_equal(run_c2c(sm, x, inverse, reorder), y)
+                sm.set_option("io", io)
+    finally:
+        sm.set_option("io", 0)
+
+
 @pytest.mark.parametrize("n", SIZES)
 def test_reorder_permutation_exact(sm, n):
     perm = O.c_reorder_index(n)
@@ -696,7 +716,7 @@ def test_first_use_selection(sm):
         sm.set_option("select_reset", 1)
 
 
-@pytest.mark.parametrize("io", [0, 1, 2])
+@pytest.mark.parametrize("io", [0, 1, 2, 3])
 @pytest.mark.parametrize("tw", [0, 1])
 @pytest.mark.parametrize("n", [8192, 16384])
 def test_c2c_beyond_the_reference(sm, n, io, tw):
