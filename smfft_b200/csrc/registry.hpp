@@ -49,11 +49,12 @@ template <int E, int MODE, int DIR, int REORDER, int IO, int TW, int REPS>
 KernelEntry make_entry()
 {
     using Tn = typename kernels::ShapeFor<E, MODE, REORDER, REPS>::type;
-    constexpr int PF = IO == kernels::IO_TMA ? Tn::PF : (Tn::PF < 0 ? 0 : Tn::PF);
+    // one buffer and TMA stores: the refill can only follow the store of the same buffer (top of the iteration)
+    constexpr int PF = IO == kernels::IO_TMA ? (Tn::STAGES == 1 ? -1 : Tn::PF) : (Tn::PF < 0 ? 0 : Tn::PF);
     constexpr int ARITH = kernels::ArithFor<E, MODE, REORDER, REPS>::value;
     KernelEntry k = make_entry_shape<E, Tn::B, Tn::TILE_E, Tn::STAGES, Tn::MINB, MODE, DIR, REORDER, IO, TW, REPS, PF, true, ARITH>();
     k.ctas = REPS > 1 ? 0 : Tn::CTAS;  // FFT_multiple is compute-bound: fill the SM
-    constexpr bool stg = (Tn::STAGES >= 2 || E == 14) && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
+    constexpr bool stg = (Tn::STAGES >= 2 || MODE == kernels::MODE_C2C) && (MODE == kernels::MODE_R2C ? Tn::STG_R2C : MODE == kernels::MODE_C2R ? Tn::STG_C2R : Tn::STG);
     k.tma_best = (IO == kernels::IO_TMA_STG) ? stg : (IO == kernels::IO_TMA ? !stg : 0);
     k.prefer = k.tma_best;
     if (kernels::RegDirect<E>::ON && kernels::RegDirect<E>::PREFER && MODE == kernels::MODE_C2C && REORDER == 1 && REPS == 1 && TW == TW_LUT) k.prefer = 0;
@@ -129,7 +130,7 @@ EntryList build_entries()
         SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_MUFU, 1);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_MUFU, 1);
         // register-output staging (TMA in, STG out), C2C and C2R
-        if constexpr (Tuning<E>::STAGES >= 2 && TuningR32<E>::STAGES >= 2) {
+        {
             SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_LUT, 1);
             SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_LUT, 1);
             SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_MUFU, 1);

@@ -63,10 +63,16 @@ struct Tuning<11> {
     static constexpr int B = 4, TILE_E = 11, F = 1, STAGES = 2, MINB = 6, CTAS = 5, PF = 1;
     static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
 };
+#ifndef SMFFT_T12_STAGES
+#define SMFFT_T12_STAGES 2
+#define SMFFT_T12_MINB 3
+#define SMFFT_T12_CTAS 3
+#define SMFFT_T12_STG 0
+#endif
 template <>
 struct Tuning<12> {
-    static constexpr int B = 4, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
-    static constexpr int STG = 0, STG_R2C = 1, STG_C2R = 0;
+    static constexpr int B = 4, TILE_E = 12, F = 1, STAGES = SMFFT_T12_STAGES, MINB = SMFFT_T12_MINB, CTAS = SMFFT_T12_CTAS, PF = 1;
+    static constexpr int STG = SMFFT_T12_STG, STG_R2C = 1, STG_C2R = 0;
 };
 
 // 8192 points (beyond the reference's range): one transform still lives in one CTA's shared memory -- a
