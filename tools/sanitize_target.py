@@ -70,6 +70,14 @@ for n in (32, 1024, 4096):
     y = torch.empty_like(x)
     sm.exec_repeated(x, y, n, nf, False, True, 0, 3)
     sm.exec_repeated(x, y, n, nf, False, False, 0, 3)
+# 8192 / 16384 points with more tiles than SMs: every persistent CTA refills its buffers (16384: the ONE buffer, behind the
+# final exchange, while the results leave from registers)
+for n, nf in ((8192, 3 * 148 + 7), (16384, 2 * 148 + 9)):
+    for io in (0, 2, 3):
+        sm.set_option("io", io)
+        run(n, nf, False, True)
+        run(n, nf, True, False)
+sm.set_option("io", 0)
 lib = ctypes.CDLL(build_compat())
 P, I = ctypes.c_void_p, ctypes.c_int
 lib.compat_ct_external.argtypes = [P, P, I, I, I, I]
