@@ -742,3 +742,58 @@ def test_c2c_beyond_the_reference(sm, n, io, tw):
         sm.exec_c2c(d, d, 32768, 1, False, True)
     sm.set_option("io", 0)
     sm.set_option("twiddle", 0)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_randomized_configurations(sm, seed):
+    """Seeded sweep over what a caller can combine: size (32..16384), batch count (odd, prime, one, many tiles per CTA), staging
+    (io 0..5), twiddle source, direction, order, in place or not, first-use selection on or off -- C2C against the FP64 DFT, and
+    R2C / C2R (64..8192 reals) against the packed FP64 forms.  A mismatch names the configuration."""
+    rng = np.random.default_rng(seed)
+    try:
+        for it in range(60):
+            n = 1 << int(rng.integers(5, 15))
+            nf = int(rng.choice([1, 2, 3, 7, 31, 127, 149, 331, 1021])) if n >= 2048 else int(rng.choice([1, 3, 17, 257, 1031, 4099]))
+            nf = min(nf, (1 << 22) // n)
+            io, tw = int(rng.integers(0, 6)), int(rng.integers(0, 2))
+            inverse, reorder, in_place = bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+            select = int(rng.integers(0, 4) == 0)
+            cfg = dict(n=n, nf=nf, io=io, tw=tw, inverse=inverse, reorder=reorder, in_place=in_place, select=select)
+            sm.set_option("io", io)
+            sm.set_option("twiddle", tw)
+            sm.set_option("select", select)
+            sm.set_option("select_min_log2_points", 10)
+            x = O.uniform_c64(nf, n, seed=seed * 1000 + it)
+            dx = to_dev(x)
+            dy = dx if in_place else torch.zeros_like(dx)
+            sm.exec_c2c(dx, dy, n, nf, inverse, reorder)
+            torch.cuda.synchronize()
+            assert O.rel_l2(c64(dy), O.ct_c2c_fp64(x, inverse, reorder)) < TOL, cfg
+            if not in_place:
+                assert np.array_equal(c64(dx), x), cfg            # the input is left alone
+        for it in range(30):
+            n = 1 << int(rng.integers(6, 14))                      # real length
+            nf = min(int(rng.choice([1, 3, 17, 149, 257, 1031])), (1 << 22) // n)
+            io, tw = int(rng.integers(0, 5)), int(rng.integers(0, 2))
+            cfg = dict(real_n=n, nf=nf, io=io, tw=tw)
+            sm.set_option("io", io)
+            sm.set_option("twiddle", tw)
+            sm.set_option("select", 0)
+            xr = O.uniform_f32(nf, n, seed=seed * 1000 + 500 + it)
+            dr = to_dev(xr)
+            dc = torch.zeros((nf, n // 2, 2), dtype=torch.float32, device="cuda")
+            sm.exec_r2c_c2r(dr, dc, n, nf, 0)
+            torch.cuda.synchronize()
+            assert O.rel_l2(c64(dc), O.r2c_packed_fp64(xr)) < TOL, cfg
+            h = O.uniform_c64(nf, n // 2, seed=seed * 1000 + 700 + it)
+            dh = to_dev(h)
+            dz = torch.zeros_like(dr)
+            sm.exec_r2c_c2r(dh, dz, n, nf, 1)
+            torch.cuda.synchronize()
+            assert O.rel_l2(dz.cpu().numpy(), O.c2r_packed_fp64(h)) < TOL, cfg
+    finally:
+        sm.set_option("io", 0)
+        sm.set_option("twiddle", 0)
+        sm.set_option("select", 0)
+        sm.set_option("select_min_log2_points", 24)
+        sm.set_option("select_reset", 1)
