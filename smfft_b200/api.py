@@ -141,7 +141,7 @@ def get_option(key: str) -> int:
 
 
 def twiddle_table() -> int:
-    """device address of the W_8192 table (for smfft::BlockFFT<..., TW_LUT> in user kernels)"""
+    """device address of the W_16384 table (for smfft::BlockFFT<..., TW_LUT> in user kernels)"""
     p = lib().smfft_twiddle_table()
     if not p:
         raise SmfftError(lib().smfft_last_error().decode())

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <vector>
 
+#include "big_fft.hpp"
 #include "registry.hpp"
 #include "tmap.hpp"
 #include "smfft.h"
@@ -40,6 +41,7 @@ static std::atomic<int> g_opt_quirk4096{0};
 static std::atomic<int> g_opt_ctas_per_sm{0};
 static std::atomic<int> g_opt_carveout{-2};  // -2: per kernel (see launch_batch), -1: driver default, 0..100: percent of shared memory
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_big_chunk_mib{1024};            // chunk of the two-pass transforms, 2^15 .. 2^18 points ("two_pass_chunk_mib")
 static std::atomic<int> g_pipe_chunk_bytes{128 << 20};  // default chunk of smfft_pipeline_host ("pipeline_chunk_mib")
 
 struct PipelineCtx {
@@ -322,6 +324,16 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     if (get_device_state(&ds)) return 1;
     if (n_points <= 0) return 0;
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail("smfft: device pointers must be 16-byte aligned");
+    if (e >= big::kMinLog2) {
+        // 2^15 .. 2^18 points: two passes over HBM (big_fft.cu), natural order, C2C
+        big::Params bp{e, dir, d_in, d_out, n_points >> e, stream, ds->tw, (long long)g_big_chunk_mib.load() << 20};
+        long long launched = 0;
+        int cuda = 0;
+        const int rc = big::exec(bp, &launched, g_err, (int)sizeof(g_err), &cuda);
+        g_launches.fetch_add(launched, std::memory_order_relaxed);
+        if (rc) g_err_code = cuda == 2 ? SMFFT_ERR_MEMORY : cuda == 1 ? SMFFT_ERR_CUDA : SMFFT_ERR_ARGUMENT;
+        return rc;
+    }
     const int opt_io = g_opt_io.load(), opt_tw = g_opt_tw.load();
     int io = reps > 1 ? kernels::IO_LDG
                       : opt_io == 0 ? -1 : opt_io == 1 ? kernels::IO_LDG : opt_io == 2 ? kernels::IO_TMA
@@ -386,7 +398,9 @@ static int timed(double* ms, const Call& c, cudaStream_t stream)
 static int c2c_call(Call* c, const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder, int reps)
 {
     const int e = ilog2_exact(fft_size);
-    if (e < 5 || e > 14 || (e >= 13 && reps > 1)) return fail("smfft: wrong FFT length %d (C2C supports 32..16384, FFT_multiple 32..4096)", fft_size);
+    if (e < 5 || e > big::kMaxLog2 || (e >= 13 && reps > 1))
+        return fail("smfft: wrong FFT length %d (C2C supports 32..262144, FFT_multiple 32..4096)", fft_size);
+    if (e >= big::kMinLog2 && !reorder) return fail("smfft: transforms of %d points (two passes) run in natural order only (reorder = 1)", fft_size);
     if (n_ffts < 0) return fail("smfft: negative nFFTs");
     int dir = inverse ? 1 : 0;
     if (g_opt_quirk4096.load() && fft_size == 4096 && inverse && !reorder) dir = 0;  // CT/SM_FFT_parameters.cuh:388
@@ -475,6 +489,7 @@ int smfft_set_option(const char* key, int value)
     if (!strcmp(key, "twiddle")) { if (value < 0 || value > 1) return fail("twiddle must be 0 or 1"); g_opt_tw = value; return 0; }
     if (!strcmp(key, "quirk_4096")) { g_opt_quirk4096 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
+    if (!strcmp(key, "two_pass_chunk_mib")) { if (value < 1 || value > 65536) return fail("two_pass_chunk_mib must be 1..65536"); g_big_chunk_mib = value; return 0; }
     if (!strcmp(key, "pipeline_chunk_mib")) { if (value < 1 || value > 1024) return fail("pipeline_chunk_mib must be 1..1024"); g_pipe_chunk_bytes = value << 20; return 0; }
     if (!strcmp(key, "carveout")) {  // experiment switch: takes effect for kernels not launched yet (or after a new process)
         if (value < -2 || value > 100) return fail("carveout must be -2 (per kernel), -1 (driver default) or 0..100");
@@ -499,6 +514,7 @@ int smfft_get_option(const char* key)
     if (!strcmp(key, "quirk_4096")) return g_opt_quirk4096;
     if (!strcmp(key, "ctas_per_sm")) return g_opt_ctas_per_sm;
     if (!strcmp(key, "carveout")) return g_opt_carveout;
+    if (!strcmp(key, "two_pass_chunk_mib")) return g_big_chunk_mib;
     if (!strcmp(key, "pipeline_chunk_mib")) return g_pipe_chunk_bytes >> 20;
     if (!strcmp(key, "device_sms")) { DeviceState* ds = nullptr; return get_device_state(&ds) ? -1 : ds->sms; }
     return -1;
@@ -732,6 +748,7 @@ int smfft_pipeline_release(void)
     }
     pipeline_free_buffers(ds->pipe);
     pipeline_free_handles(ds->pipe);
+    smfft::big::release();  // twiddle tables and scratch pool of the two-pass transforms
     return 0;
 }
 

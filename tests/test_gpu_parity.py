@@ -739,7 +739,7 @@ def test_c2c_beyond_the_reference(sm, n, io, tw):
     with pytest.raises(sm.SmfftError):
         sm.FFT_multiple_benchmark(d, d, n, 200, False, True)      # the repeated benchmark stops at 4096 points
     with pytest.raises(sm.SmfftError):
-        sm.exec_c2c(d, d, 32768, 1, False, True)
+        sm.exec_c2c(d, d, 1 << 19, 1, False, True)              # two-pass transforms stop at 2^18 points
     sm.set_option("io", 0)
     sm.set_option("twiddle", 0)
 
@@ -797,3 +797,61 @@ def test_randomized_configurations(sm, seed):
         sm.set_option("select", 0)
         sm.set_option("select_min_log2_points", 24)
         sm.set_option("select_reset", 1)
+
+
+@pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 17, 1 << 18])
+def test_two_pass_transforms(sm, n):
+    """2^15 .. 2^18 points (beyond the reference, SURVEY.md 8f-4 "N > 4096 via multi-pass"): N = N1 N2 in two passes over HBM
+    (csrc/big_fft.cu), strided TMA boxes, twiddles from a two-level FP64-rounded table.  Both directions against the FP64 DFT;
+    batches of 1, 5 and 37; chunked (scratch smaller than the batch); in place; the host-timed entry point; error contract."""
+    try:
+        for nf in (1, 5, 37):
+            x = O.uniform_c64(nf, n, seed=n % 1000 + nf)
+            for inverse in (False, True):
+                assert O.rel_l2(run_c2c(sm, x, inverse, True), O.ct_c2c_fp64(x, inverse, True)) < TOL, (n, nf, inverse)
+        x = O.uniform_c64(11, n, seed=3)
+        want = O.ct_c2c_fp64(x, False, True)
+        sm.set_option("two_pass_chunk_mib", 1)                       # 1 MiB of scratch: 11 transforms in several chunks
+        assert O.rel_l2(run_c2c(sm, x, False, True), want) < TOL
+        d = to_dev(x)
+        sm.exec_c2c(d, d, n, 11, False, True)                         # in place, chunked
+        torch.cuda.synchronize()
+        assert O.rel_l2(c64(d), want) < TOL
+        sm.set_option("two_pass_chunk_mib", 1024)
+        d = to_dev(x)
+        out = torch.zeros_like(d)
+        assert sm.FFT_external_benchmark(d, out, n, 11, False, True) > 0
+        torch.cuda.synchronize()
+        assert O.rel_l2(c64(out), want) < TOL
+        assert np.array_equal(c64(d), x)                              # the input is left alone
+        # one-hot at p: X[k] = W_N^(p k) -- pins the order of the output exactly
+        p = 12345 % n
+        hot = np.zeros((1, n), dtype=np.complex64)
+        hot[0, p] = 1
+        y = run_c2c(sm, hot, False, True)[0]
+        k = np.arange(n)
+        assert np.max(np.abs(y - np.exp(-2j * np.pi * ((p * k) % n) / n))) < 1e-5
+        with pytest.raises(sm.SmfftError, match="natural order"):
+            sm.exec_c2c(d, out, n, 11, False, False)                  # no bit-reversed-input flavour for two-pass sizes
+        with pytest.raises(sm.SmfftError):
+            sm.FFT_multiple_benchmark(d, out, n, 200, False, True)
+    finally:
+        sm.set_option("two_pass_chunk_mib", 1024)
+
+
+def test_two_pass_full_size_round_trip(sm):
+    """65536 points on the full 4 GiB batch: inverse(forward(x)) = N x on rows sampled across the batch, and the forward
+    spectrum of the first / middle / last transforms against FP64."""
+    n = 1 << 16
+    nf = (1 << 29) // n
+    x = torch.rand((nf, n, 2), device="cuda")
+    y = torch.empty_like(x)
+    sm.exec_c2c(x, y, n, nf, False, True)
+    rows = [0, 1, nf // 2, nf - 2, nf - 1]
+    for r in rows:
+        xr = c64(x[r:r + 1])
+        assert O.rel_l2(c64(y[r:r + 1]), O.ct_c2c_fp64(xr, False, True)) < TOL, r
+    sm.exec_c2c(y, y, n, nf, True, True)                              # in place, inverse
+    torch.cuda.synchronize()
+    for r in rows + list(range(7, nf, nf // 13)):
+        assert O.rel_l2(c64(y[r:r + 1]) / n, c64(x[r:r + 1])) < TOL, r
