@@ -370,6 +370,8 @@ def other_modes(x, y, reps=5):
     (16 B per complex point, 8 B per real point)."""
     import math
 
+    import torch
+
     import smfft_b200 as sm
 
     peak, _ = measured_peak()
@@ -392,6 +394,34 @@ def other_modes(x, y, reps=5):
         for nbig in (8192, 16384):   # beyond the reference: one transform per 64 / 128 KB tile
             out[f"c2c_{nbig}"] = {("reorder" if r else "noreorder"): row(med(lambda: sm.FFT_external_benchmark(x, y, nbig, BATCH_POINTS // nbig, False, bool(r))), BATCH_POINTS * 16)
                                   for r in (1, 0)}
+        # 2^15 .. 2^18 points: two passes over HBM (csrc/big_fft.cu) -- 32 algorithmic bytes per point; cuFFT's plan for
+        # the same batch on the same buffers beside it (it also makes two passes at these sizes)
+        out["c2c_two_pass"] = {"how": "FFT_external_benchmark, natural order, 4 GiB batch, scratch chunk 1 GiB; frac = 32 B/point over the measured copy peak"}
+        try:
+            import ctypes
+            cu = ctypes.CDLL("libcufft.so.11")
+        except OSError:
+            cu = None
+        for nbig in (1 << 15, 1 << 16, 1 << 17, 1 << 18):
+            ms = med(lambda: sm.FFT_external_benchmark(x, y, nbig, BATCH_POINTS // nbig, False, True))
+            r = {"ms": round(ms, 4), "GBps_traffic": round(BATCH_POINTS * 32 / ms / 1e6, 1), "frac": round(BATCH_POINTS * 32 / ms / 1e6 / peak, 4)}
+            if cu is not None:
+                h = ctypes.c_int(0)
+                if cu.cufftPlan1d(ctypes.byref(h), nbig, 0x29, BATCH_POINTS // nbig) == 0:
+                    xp, yp = ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr())
+
+                    def cufft_once():
+                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                        ev[0].record()
+                        cu.cufftExecC2C(h, xp, yp, -1)
+                        ev[1].record()
+                        torch.cuda.synchronize()
+                        return ev[0].elapsed_time(ev[1])
+
+                    r["cufft_ms"] = round(med(cufft_once), 4)
+                    r["ours_vs_cufft"] = round(r["cufft_ms"] / ms, 4)
+                    cu.cufftDestroy(h)
+            out["c2c_two_pass"][str(nbig)] = r
         real_points = 2 * BATCH_POINTS          # the same 4 GiB read as floats
         for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
             nf = real_points // n

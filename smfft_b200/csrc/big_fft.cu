@@ -9,7 +9,9 @@
 //           positions (n1 + N1 k2) of a scratch buffer.  A CTA owns 16 consecutive n1: its tile is a TMA box of N2 rows x 128
 //           bytes with a row pitch of N1 * 8 bytes -- strided in HBM, dense (SWIZZLE_128B) in shared memory.
 //   pass B: for every k2 a transform of length N1 over n1 (contiguous), written to X[N2 k1 + k2].  A CTA owns 16 consecutive
-//           k2: it reads 16 contiguous rows straight into registers and writes a TMA box of N1 rows x 128 bytes, pitch N2 * 8.
+//           k2: it reads 16 contiguous transforms (one TMA box of N1 rows x 128 bytes, dense) and writes a TMA box of N1 rows
+//           x 128 bytes with a row pitch of N2 * 8 bytes.  (Reading the rows straight into registers instead: 2.81 / 2.87 ms
+//           against 2.65 / 2.62 ms at 2^15 / 2^16 points, profiles/r02_ab_two_pass.json.)
 //
 // Both passes are user kernels of the library's own device primitive (smfft::BlockFFT, include/smfft/device.cuh): 16
 // transforms per block, 16 points per thread, registers in and out; the shared-memory tile is the TMA landing zone, then the
@@ -37,15 +39,15 @@ namespace big {
 namespace {
 
 struct PassArgs {
-    alignas(64) CUtensorMap in_map;   // pass A: [N2 * ffts rows][N1 points]
+    alignas(64) CUtensorMap in_map;   // pass A: [N2 * ffts rows][N1 points]; pass B: the scratch as rows of 128 bytes
     alignas(64) CUtensorMap out_map;  // pass A: the same geometry over the scratch; pass B: [N1 * ffts rows][N2 points]
-    const float2* gin;                // pass B: the scratch, read as contiguous rows
     const float2* base_tw;            // W_16384 table (twiddles of the block transforms)
     const float2* wt;                 // pass A: W_N^j, j < 512, then W_N^(512 j), j < N / 512
     int groups;                       // tiles per transform: N1 / 16 (pass A), N2 / 16 (pass B)
 };
 
-// one tile = 16 transforms of 2^LOG2LEN points.  PASS 0 = A (strided box in, twiddle, same box out), 1 = B (rows in, box out)
+// one tile = 16 transforms of 2^LOG2LEN points.  PASS 0 = A (strided box in, twiddle, same box out), 1 = B (16 contiguous
+// transforms in -- in_map: the scratch as rows of 128 bytes --, strided box out)
 template <int LOG2LEN, int DIR, int PASS>
 __global__ void __launch_bounds__((LOG2LEN >= 9 ? 256 : (1 << LOG2LEN)), (LOG2LEN <= 7 ? 8 : LOG2LEN == 8 ? 4 : 2)) big_pass_kernel(const __grid_constant__ PassArgs a)
 {
@@ -65,23 +67,27 @@ __global__ void __launch_bounds__((LOG2LEN >= 9 ? 256 : (1 << LOG2LEN)), (LOG2LE
     const int row0 = fft * LEN;  // first row of this transform in the strided matrix
 
     float2 v[R];
-    if constexpr (PASS == 0) {
-        if (tid == 0) {
-            plat::mbar_init(bar, 1);
-            plat::mbar_fence_init();
-            plat::mbar_arrive_expect_tx(bar, TILE * 8);
+    if (tid == 0) {
+        plat::mbar_init(bar, 1);
+        plat::mbar_fence_init();
+        plat::mbar_arrive_expect_tx(bar, TILE * 8);
 #pragma unroll
-            for (int b = 0; b < NBOX; b++) plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, 32 * g, row0 + b * BOX_ROWS, bar);
+        for (int b = 0; b < NBOX; b++) {
+            if constexpr (PASS == 0)
+                plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, 32 * g, row0 + b * BOX_ROWS, bar);
+            else
+                plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, 0, (int)(id * LEN) + b * BOX_ROWS, bar);  // 16 contiguous transforms = LEN rows of 128 bytes
         }
-        F::fill_twiddles(stw, a.base_tw);
-        __syncthreads();  // barrier initialised, table filled
-        plat::mbar_wait(bar, 0);
+    }
+    F::fill_twiddles(stw, a.base_tw);
+    __syncthreads();  // barrier initialised, table filled
+    plat::mbar_wait(bar, 0);
+    if constexpr (PASS == 0) {
 #pragma unroll
-        for (int m = 0; m < R; m++) v[m] = tile[SW::phys((t + m * T) * 16 + f)];
+        for (int m = 0; m < R; m++) v[m] = tile[SW::phys((t + m * T) * 16 + f)];  // column f of the box
     } else {
-        F::load(v, a.gin + id * TILE);  // coalesced: 16 lanes of a transform read 128 contiguous bytes
-        F::fill_twiddles(stw, a.base_tw);
-        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < R; m++) v[m] = tile[SW::phys(F::index(m))];  // transform f of the tile: 16 lanes read one 128-byte row
     }
 
     F::exec(v, tile, stw);  // synchronises before its first write to the tile: every thread has its points in registers
@@ -259,7 +265,10 @@ int exec(const Params& p, long long* launches, char* err, int errcap, int* cuda)
         PassArgs b;
         memset(&b, 0, sizeof(b));
         b.base_tw = (const float2*)p.base_tw;
-        b.gin = scratch;
+        if (host::encode_tile_map(&b.in_map, scratch, cf * N / 16, N1 > 256 ? 256 : (int)N1)) {
+            rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (two-pass transform, pass B input)%s", "");
+            break;
+        }
         r1 = host::encode_strided_map(&b.out_map, out, 2 * N2, N1 * cf, N1 > 256 ? 256 : (int)N1);
         if (r1) { rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (two-pass transform, pass B)%s", ""); break; }
         b.groups = (int)(N2 / 16);
