@@ -38,6 +38,14 @@ namespace big {
 
 namespace {
 
+#ifndef SMFFT_BIG_R32_512
+#define SMFFT_BIG_R32_512 1  // 512-point passes: 32 points per thread (16 lanes per transform) instead of 16 (32 lanes)
+#endif
+#ifndef SMFFT_BIG_SPLIT17
+#define SMFFT_BIG_SPLIT17 8  // log2 of the strided pass (A) at 2^17 points: 8 (256 x 512) or 9 (512 x 256)
+#endif
+SMFFT_CX int log2r_for(int log2len) { return (log2len >= 9 && SMFFT_BIG_R32_512) ? 5 : 4; }
+
 struct PassArgs {
     alignas(64) CUtensorMap in_map;   // pass A: [N2 * ffts rows][N1 points]; pass B: the scratch as rows of 128 bytes
     alignas(64) CUtensorMap out_map;  // pass A: the same geometry over the scratch; pass B: [N1 * ffts rows][N2 points]
@@ -49,13 +57,13 @@ struct PassArgs {
 // one tile = 16 transforms of 2^LOG2LEN points.  PASS 0 = A (strided box in, twiddle, same box out), 1 = B (16 contiguous
 // transforms in -- in_map: the scratch as rows of 128 bytes --, strided box out)
 template <int LOG2LEN, int DIR, int PASS>
-__global__ void __launch_bounds__((LOG2LEN >= 9 ? 256 : (1 << LOG2LEN)), (LOG2LEN <= 7 ? 8 : LOG2LEN == 8 ? 4 : 2)) big_pass_kernel(const __grid_constant__ PassArgs a)
+__global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2LEN <= 7 ? 8 : LOG2LEN == 8 ? 4 : 2)) big_pass_kernel(const __grid_constant__ PassArgs a)
 {
-    using F = BlockFFT<LOG2LEN, DIR, 16, TW_LUT, (LOG2LEN >= 9 ? 5 : 4)>;  // 512 points: 32 per thread, so a transform keeps 16 lanes
+    using F = BlockFFT<LOG2LEN, DIR, 16, TW_LUT, log2r_for(LOG2LEN)>;  // 512 points: 32 per thread, so a transform keeps 16 lanes
     using SW = detail::LayoutSW128;
     constexpr int LEN = 1 << LOG2LEN, TILE = 16 * LEN, T = F::T, R = F::R;
     constexpr int BOX_ROWS = LEN > 256 ? 256 : LEN, NBOX = LEN / BOX_ROWS;
-    static_assert(F::THREADS == 16 * T && T <= 16, "16 transforms per block, at most 16 lanes each (conflict-free columns)");
+    static_assert(F::THREADS == 16 * T, "16 transforms per block");
     extern __shared__ unsigned char raw[];
     unsigned char* smem = raw + ((1024u - (plat::smem_u32(raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs a 1 KB aligned tile
     float2* tile = reinterpret_cast<float2*>(smem);
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__((LOG2LEN >= 9 ? 256 : (1 << LOG2LEN)), (LOG2LE
 template <int LOG2LEN>
 constexpr int pass_smem_bytes()
 {
-    return 16 * (1 << LOG2LEN) * 8 + 64 + ((BlockFFT<LOG2LEN, 0, 16, TW_LUT, (LOG2LEN >= 9 ? 5 : 4)>::TWIDDLE_POINTS * 8 + 127) & ~127) + 1024;
+    return 16 * (1 << LOG2LEN) * 8 + 64 + ((BlockFFT<LOG2LEN, 0, 16, TW_LUT, log2r_for(LOG2LEN)>::TWIDDLE_POINTS * 8 + 127) & ~127) + 1024;
 }
 
 typedef void (*PassFn)(const PassArgs);
@@ -144,7 +152,7 @@ PassInfo pass_info(int dir, int pass)
 {
     PassFn fn = dir ? (pass ? big_pass_kernel<LOG2LEN, 1, 1> : big_pass_kernel<LOG2LEN, 1, 0>)
                     : (pass ? big_pass_kernel<LOG2LEN, 0, 1> : big_pass_kernel<LOG2LEN, 0, 0>);
-    return PassInfo{fn, LOG2LEN >= 9 ? 256 : (1 << LOG2LEN), pass_smem_bytes<LOG2LEN>()};
+    return PassInfo{fn, 16 << (LOG2LEN - log2r_for(LOG2LEN)), pass_smem_bytes<LOG2LEN>()};
 }
 
 PassInfo pass_for(int log2len, int dir, int pass)
@@ -183,7 +191,7 @@ int failf(char* err, int cap, int* cuda, int code, const char* fmt, const char* 
 // the factorisation: N2 = length of pass A (strided), N1 = length of pass B (contiguous)
 static void split(int e, int* log2_n2, int* log2_n1)
 {
-    *log2_n2 = e == 18 ? 9 : 8;
+    *log2_n2 = e == 18 ? 9 : e == 17 ? SMFFT_BIG_SPLIT17 : 8;
     *log2_n1 = e - *log2_n2;
 }
 
