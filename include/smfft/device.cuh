@@ -22,6 +22,8 @@
 //   convolve<<<n_transforms / F::FFTS, F::THREADS>>>(x, H, y);
 // (smfft::block_convolve below is exactly this with the pointwise step as a functor; tests/compat/compat_kernels.cu and
 // tools/convolve_bench.py use and time it against the reference's own device function in the same user kernel.)
+// The library's own two-pass transforms of 2^15 .. 2^18 points (smfft_b200/csrc/big_fft.cu) are user kernels of this primitive
+// too: 16 transforms per block read from a TMA-loaded tile, exec(), a twiddle multiply on the registers, TMA store.
 //
 // CONTRACT
 //   * blockDim.x == THREADS = FFTS * N / R (1-D block), every thread of the block calls exec() (it contains __syncthreads);

@@ -1,0 +1,58 @@
+"""CPU model of the two-pass (four-step) factorisation that smfft_b200/csrc/big_fft.cu runs for 2^15 .. 2^18 points: the same index
+conventions (n = n1 + N1 n2, k = N2 k1 + k2), the same split of the sizes, the same two-level FP64-rounded twiddle table
+(W_N^j for j < 512 and W_N^(512 j)) evaluated in float32 -- against numpy's FP64 FFT.  Pins the algebra and the table layout
+without a GPU; the kernels themselves are checked by tests/test_gpu_parity.py::test_two_pass_transforms."""
+import numpy as np
+import pytest
+
+
+def split(e):
+    """log2 of (N2 = strided pass A, N1 = contiguous pass B), as big_fft.cu"""
+    l2 = 9 if e == 18 else 8
+    return l2, e - l2
+
+
+def two_level_table(n):
+    j = np.arange(512)
+    lo = np.exp(-2j * np.pi * j / n).astype(np.complex64)
+    hi = np.ones(512, dtype=np.complex64)
+    m = n // 512
+    hi[:m] = np.exp(-2j * np.pi * j[:m] * 512.0 / n).astype(np.complex64)
+    return lo, hi
+
+
+def two_pass(x, inverse):
+    n = x.shape[-1]
+    e = n.bit_length() - 1
+    l2, l1 = split(e)
+    n2, n1 = 1 << l2, 1 << l1
+    lo, hi = two_level_table(n)
+    a = x.reshape(-1, n2, n1)                                    # [fft][n2][n1]: n = n1 + N1 n2
+    fa = (np.fft.ifft(a, axis=1) * n2 if inverse else np.fft.fft(a, axis=1)).astype(np.complex64)   # pass A: over n2 -> [fft][k2][n1]
+    p = np.arange(n2)[:, None] * np.arange(n1)[None, :]          # n1 k2 < N
+    assert p.max() < n and (p >> 9).max() < max(1, n // 512)
+    w = (lo[p & 511] * hi[p >> 9]).astype(np.complex64)          # the kernel's W(p) = lo[p & 511] * hi[p >> 9]
+    if inverse:
+        w = np.conj(w)
+    b = fa * w[None]
+    fb = (np.fft.ifft(b, axis=2) * n1 if inverse else np.fft.fft(b, axis=2)).astype(np.complex64)   # pass B: over n1 -> [fft][k2][k1]
+    return np.transpose(fb, (0, 2, 1)).reshape(-1, n)            # X[N2 k1 + k2]: rows k1, columns k2
+
+
+@pytest.mark.parametrize("e", [15, 16, 17, 18])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_factorisation_and_twiddle_table(e, inverse):
+    n = 1 << e
+    rng = np.random.default_rng(e)
+    x = rng.random((2, n, 2), dtype=np.float32).view(np.complex64).reshape(2, n)
+    want = np.fft.ifft(x.astype(np.complex128), axis=-1) * n if inverse else np.fft.fft(x.astype(np.complex128), axis=-1)
+    got = two_pass(x, inverse)
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert rel < 1e-6, rel
+
+
+def test_split_covers_the_range():
+    for e in range(15, 19):
+        l2, l1 = split(e)
+        assert l1 + l2 == e and 7 <= l1 <= 9 and 8 <= l2 <= 9     # block transforms of 128 .. 512 points, 16 per tile
+        assert (1 << e) // 512 <= 512                              # the upper table has at most 512 entries
