@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
 echo "=== pytest"; timeout 2400 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tee gpurun_out/r02_pytest_final.log | tail -4
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 echo "=== bench"; timeout 900 python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; echo "bench rc=$?"; tail -3 gpurun_out/r02_bench_final.err; python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_final.json')); print(d['value'], d['ms_per_4GiB_batch'], d['roofline']['frac'], d['roofline']['traffic'], d['roofline']['best_known']); print({k:v['ms'] for k,v in d['per_size'].items()}); print(d['e2e']['value'], d['e2e']['frac'], d['clocks'], d['cpu_baseline']['value']); o=d['other_modes']; print({k:v['ms'] for k,v in o['r2c'].items()}); print({k:v['ms'] for k,v in o['c2r'].items()}); print({k:(v['ms'],v['TFLOPs']) for k,v in o['ct_multiple'].items()}); print(o['c2c_8192'], o['c2c_16384']); print(d['baselines']['steady_state_per_kernel']); print(d['device_api']['external']['worst_speedup'], d['device_api']['multiple']['worst_speedup'])"
+import json; d=json.load(open('gpurun_out/r02_bench_final.json')); print(d['value'], d['ms_per_4GiB_batch'], d['roofline']['frac'], d['roofline']['traffic'], d['roofline']['best_known']); print({k:v['ms'] for k,v in d['per_size'].items()}); print(d['e2e']['value'], d['e2e']['frac'], d['clocks'], d['cpu_baseline']['value']); o=d['other_modes']; print({k:v['ms'] for k,v in o['r2c'].items()}); print({k:v['ms'] for k,v in o['c2r'].items()}); print({k:(v['ms'],v['TFLOPs']) for k,v in o['ct_multiple'].items()}); print(o['c2c_8192'], o['c2c_16384']); print(o['c2c_two_pass']); print(d['baselines']['steady_state_per_kernel']); print(d['device_api']['external']['worst_speedup'], d['device_api']['multiple']['worst_speedup'])"
 echo "=== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_final_ref.json 2>&1; tail -c 300 gpurun_out/r02_bench_final_ref.json
 echo "=== ncu launch list (bench)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_ncu_launches_final.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-baselines --no-other-modes --no-device-api > gpurun_out/r02_ncu_bench_final.log 2>&1; echo "rc=$?"
