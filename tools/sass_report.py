@@ -60,11 +60,21 @@ def main():
             continue
         label = f"{MODES[int(mode)]} N={1 << int(e)} {'reorder' if int(r) else 'no-reorder'} R={1 << int(b)} F={f} io={IOS[int(io)]} reps={reps} arith={arith} minb={minb}"
         rows.append(((int(mode), int(reps), int(e), -int(r), int(io)), row(label, c)))
+    big = []
+    for name, c in functions(lib):
+        m = re.search(r"big_pass_kernelILi(\d+)ELi(\d+)ELi(\d+)E", name)
+        if m and int(m.group(2)) == 0:
+            big.append((int(m.group(1)), int(m.group(3)), row(f"two-pass C2C, pass {'AB'[int(m.group(3))]}, {1 << int(m.group(1))}-point block transforms x 16 per tile", c)))
     print("## libsmfft.so -- totals over ALL instances: " + ", ".join(f"{k} {tot[k]}" for k in ("UTMALDG", "UTMASTG", "SYNCS", "FADD2", "SHFL")) + "\n")
     print("Forward (C2R: inverse), table twiddles; every staging variant compiled into the library:\n")
     print(hdr)
     for _, r_ in sorted(rows):
         print(r_)
+    if big:
+        print("\n## two-pass transforms of 2^15 .. 2^18 points (csrc/big_fft.cu, forward): TMA box in, TMA box out\n")
+        print(hdr)
+        for _, _, r_ in sorted(big):
+            print(r_)
     so = os.path.join(ROOT, "tests", "compat", "_build", "libcompat_kernels.so")
     if os.path.exists(so):
         print("\n## reference-contract wrapper kernels (include/smfft/compat.cuh) and the native device primitive (include/smfft/device.cuh)\n")
