@@ -746,18 +746,20 @@ def test_c2c_beyond_the_reference(sm, n, io, tw):
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
 def test_randomized_configurations(sm, seed):
-    """Seeded sweep over what a caller can combine: size (32..16384), batch count (odd, prime, one, many tiles per CTA), staging
+    """Seeded sweep over what a caller can combine: size (32..262144), batch count (odd, prime, one, many tiles per CTA), staging
     (io 0..5), twiddle source, direction, order, in place or not, first-use selection on or off -- C2C against the FP64 DFT, and
     R2C / C2R (64..8192 reals) against the packed FP64 forms.  A mismatch names the configuration."""
     rng = np.random.default_rng(seed)
     try:
         for it in range(60):
-            n = 1 << int(rng.integers(5, 15))
+            n = 1 << int(rng.integers(5, 19))                       # 32 .. 262144 (two passes from 32768 up)
             nf = int(rng.choice([1, 2, 3, 7, 31, 127, 149, 331, 1021])) if n >= 2048 else int(rng.choice([1, 3, 17, 257, 1031, 4099]))
-            nf = min(nf, (1 << 22) // n)
+            nf = max(1, min(nf, (1 << 22) // n))
             io, tw = int(rng.integers(0, 6)), int(rng.integers(0, 2))
             inverse, reorder, in_place = bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+            reorder = reorder or n >= (1 << 15)                      # the two-pass sizes take natural-order input only
             select = int(rng.integers(0, 4) == 0)
+            sm.set_option("two_pass_chunk_mib", int(rng.choice([1, 4, 1024])))
             cfg = dict(n=n, nf=nf, io=io, tw=tw, inverse=inverse, reorder=reorder, in_place=in_place, select=select)
             sm.set_option("io", io)
             sm.set_option("twiddle", tw)
@@ -797,6 +799,7 @@ def test_randomized_configurations(sm, seed):
         sm.set_option("select", 0)
         sm.set_option("select_min_log2_points", 24)
         sm.set_option("select_reset", 1)
+        sm.set_option("two_pass_chunk_mib", 1024)
 
 
 @pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 17, 1 << 18])
