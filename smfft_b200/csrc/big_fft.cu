@@ -39,7 +39,8 @@ namespace big {
 namespace {
 
 #ifndef SMFFT_BIG_R32_512
-#define SMFFT_BIG_R32_512 1  // 512-point passes: 32 points per thread (16 lanes per transform) instead of 16 (32 lanes)
+#define SMFFT_BIG_R32_512 1  // 512-point passes: 32 points per thread (16 lanes per transform) instead of 16 (32 lanes): 2.95 / 3.08 vs 3.16 / 3.58 ms;
+                             // persistent CTAs with three 64 KB buffers instead of one tile per CTA: 2.96 / 3.11 ms, no gain (profiles/r02_ab_two_pass.json)
 #endif
 #ifndef SMFFT_BIG_SPLIT17
 #define SMFFT_BIG_SPLIT17 8  // log2 of the strided pass (A) at 2^17 points: 8 (256 x 512) or 9 (512 x 256)
