@@ -394,17 +394,19 @@ def other_modes(x, y, reps=5):
         for nbig in (8192, 16384):   # beyond the reference: one transform per 64 / 128 KB tile
             out[f"c2c_{nbig}"] = {("reorder" if r else "noreorder"): row(med(lambda: sm.FFT_external_benchmark(x, y, nbig, BATCH_POINTS // nbig, False, bool(r))), BATCH_POINTS * 16)
                                   for r in (1, 0)}
-        # 2^15 .. 2^18 points: two passes over HBM (csrc/big_fft.cu) -- 32 algorithmic bytes per point; cuFFT's plan for
-        # the same batch on the same buffers beside it (it also makes two passes at these sizes)
-        out["c2c_two_pass"] = {"how": "FFT_external_benchmark, natural order, 4 GiB batch, scratch chunk 1 GiB; frac = 32 B/point over the measured copy peak"}
+        # 2^15 .. 2^24 points: two or three passes over HBM (csrc/big_fft.cu) -- 32 / 48 algorithmic bytes per point; cuFFT's
+        # plan for the same batch on the same buffers beside it
+        out["c2c_two_pass"] = {"how": "FFT_external_benchmark, natural order, 4 GiB batch, scratch chunk 1 GiB; two passes up to 2^18 points, three from 2^19; "
+                                      "frac = 32 (48) B/point over the measured copy peak"}
         try:
             import ctypes
             cu = ctypes.CDLL("libcufft.so.11")
         except OSError:
             cu = None
-        for nbig in (1 << 15, 1 << 16, 1 << 17, 1 << 18):
+        for nbig in (1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 20, 1 << 24):
             ms = med(lambda: sm.FFT_external_benchmark(x, y, nbig, BATCH_POINTS // nbig, False, True))
-            r = {"ms": round(ms, 4), "GBps_traffic": round(BATCH_POINTS * 32 / ms / 1e6, 1), "frac": round(BATCH_POINTS * 32 / ms / 1e6 / peak, 4)}
+            bpp = 32 if nbig <= (1 << 18) else 48
+            r = {"ms": round(ms, 4), "passes": bpp // 16, "GBps_traffic": round(BATCH_POINTS * bpp / ms / 1e6, 1), "frac": round(BATCH_POINTS * bpp / ms / 1e6 / peak, 4)}
             if cu is not None:
                 h = ctypes.c_int(0)
                 if cu.cufftPlan1d(ctypes.byref(h), nbig, 0x29, BATCH_POINTS // nbig) == 0:

@@ -48,15 +48,21 @@ namespace {
 SMFFT_CX int log2r_for(int log2len) { return (log2len >= 9 && SMFFT_BIG_R32_512) ? 5 : 4; }
 
 struct PassArgs {
-    alignas(64) CUtensorMap in_map;   // pass A: [N2 * ffts rows][N1 points]; pass B: the scratch as rows of 128 bytes
-    alignas(64) CUtensorMap out_map;  // pass A: the same geometry over the scratch; pass B: [N1 * ffts rows][N2 points]
+    alignas(64) CUtensorMap in_map;   // column pass: [rows][row_len points]; row pass: the scratch as rows of 128 bytes
+    alignas(64) CUtensorMap out_map;  // column pass: the same geometry over the destination; row pass: [LEN * ffts rows][out_row_len points]
     const float2* base_tw;            // W_16384 table (twiddles of the block transforms)
-    const float2* wt;                 // pass A: W_N^j, j < 512, then W_N^(512 j), j < N / 512
-    int groups;                       // tiles per transform: N1 / 16 (pass A), N2 / 16 (pass B)
+    const float2* wt;                 // column pass: W_M^j (j < 512), W_M^(512 j), W_M^(2^18 j) -- M = the modulus of this pass's twiddles
+    int groups;                       // column pass: 16-column groups per row; row pass: 16-transform groups per (transform, kmid)
+    // column pass: tile id -> slab = id / groups (LEN consecutive rows), g = id % groups; the value at (row k, column c) is
+    // multiplied by W_M^(cidx (kfix + kscale k)), cidx = c >> col_shift, kfix = slab % kdiv
+    int col_shift, kdiv, kscale;
+    // row pass: tile id -> g = id % groups, kmid = (id / groups) % nmid, fft = id / (groups nmid); transform j of the tile is
+    // transform kmid + nmid (16 g + j + 16 groups fft) of the scratch; column offset of the output box = out_col_scale * kmid
+    int nmid, out_col_scale;
 };
 
-// one tile = 16 transforms of 2^LOG2LEN points.  PASS 0 = A (strided box in, twiddle, same box out), 1 = B (16 contiguous
-// transforms in -- in_map: the scratch as rows of 128 bytes --, strided box out)
+// one tile = 16 transforms of 2^LOG2LEN points.  PASS 0 = column pass (strided box in, twiddle, same box out), 1 = row pass
+// (16 transforms in -- contiguous, or gathered one box each when nmid > 1 --, strided box out)
 template <int LOG2LEN, int DIR, int PASS>
 __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2LEN <= 7 ? 8 : LOG2LEN == 8 ? 4 : 2)) big_pass_kernel(const __grid_constant__ PassArgs a)
 {
@@ -71,25 +77,42 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TILE * 8);
     float2* stw = reinterpret_cast<float2*>(smem + TILE * 8 + 64);
     const int tid = threadIdx.x, f = tid / T, t = tid & (T - 1);
-    const long long id = blockIdx.x;
-    const int fft = (int)(id / a.groups), g = (int)(id % a.groups);
-    const int row0 = fft * LEN;  // first row of this transform in the strided matrix
+    const unsigned id = blockIdx.x;  // tile ids fit 32 bits (the grid does): 32-bit divisions only
+    const int g = (int)(id % (unsigned)a.groups);
+    const unsigned slab = id / (unsigned)a.groups;  // column pass: which LEN rows; row pass: fft * nmid + kmid
+    int out_c0, out_row0;
+    if constexpr (PASS == 0) {
+        out_c0 = 32 * g;
+        out_row0 = (int)(slab * LEN);
+    } else {
+        const int kmid = (int)(slab % (unsigned)a.nmid);
+        out_c0 = 32 * g + 2 * a.out_col_scale * kmid;
+        out_row0 = (int)(slab / (unsigned)a.nmid) * LEN;
+    }
 
     float2 v[R];
     if (tid == 0) {
         plat::mbar_init(bar, 1);
         plat::mbar_fence_init();
+    }
+    __syncthreads();  // the barrier is initialised for every thread (and for the tools) before its first use
+    if (tid == 0) {
         plat::mbar_arrive_expect_tx(bar, TILE * 8);
+        if constexpr (PASS == 0) {
 #pragma unroll
-        for (int b = 0; b < NBOX; b++) {
-            if constexpr (PASS == 0)
-                plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, 32 * g, row0 + b * BOX_ROWS, bar);
-            else
-                plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, 0, (int)(id * LEN) + b * BOX_ROWS, bar);  // 16 contiguous transforms = LEN rows of 128 bytes
+            for (int b = 0; b < NBOX; b++) plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, out_c0, out_row0 + b * BOX_ROWS, bar);
+        } else if (a.nmid == 1) {
+#pragma unroll
+            for (int b = 0; b < NBOX; b++) plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, 0, (int)(id * (unsigned)LEN) + b * BOX_ROWS, bar);  // 16 contiguous transforms = LEN rows of 128 bytes
+        } else {
+            // gathered: transform j of the tile is LEN / 16 rows of 128 bytes somewhere in the scratch, one box each
+            const unsigned fft = slab / (unsigned)a.nmid, kmid = slab % (unsigned)a.nmid;
+            const long long tr0 = kmid + (long long)a.nmid * (16 * g + 16LL * a.groups * fft);
+            for (int j = 0; j < 16; j++) plat::tma_load_2d(tile + j * LEN, &a.in_map, 0, (int)((tr0 + (long long)a.nmid * j) * (LEN / 16)), bar);
         }
     }
     F::fill_twiddles(stw, a.base_tw);
-    __syncthreads();  // barrier initialised, table filled
+    __syncthreads();  // table filled
     plat::mbar_wait(bar, 0);
     if constexpr (PASS == 0) {
 #pragma unroll
@@ -102,16 +125,18 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
     F::exec(v, tile, stw);  // synchronises before its first write to the tile: every thread has its points in registers
 
     if constexpr (PASS == 0) {
-        // W_N^(n1 k2), k2 = t + m T = W^(n1 t) (W^(n1 T))^m: an accurate base and an accurate step from the two-level table,
-        // the powers four at a time (at most R/4 + 2 roundings deep)
-        const int n1 = 16 * g + f;
-        auto W = [&](int p) {
-            float2 w = detail::cmul(__ldg(a.wt + (p & 511)), __ldg(a.wt + 512 + (p >> 9)));
+        // W_M^(cidx (kfix + kscale k)), k = t + m T: an accurate base and an accurate step from the three-level table, the
+        // powers four at a time (at most R/4 + 2 roundings deep)
+        const unsigned cidx = (unsigned)(16 * g + f) >> a.col_shift;
+        auto W = [&](unsigned p) {  // p < M <= 2^24
+            float2 w = detail::cmul(__ldg(a.wt + (p & 511)), __ldg(a.wt + 512 + ((p >> 9) & 511)));
+            w = detail::cmul(w, __ldg(a.wt + 1024 + (p >> 18)));
             if (DIR) w.y = -w.y;
             return w;
         };
-        const float2 s1 = W(n1 * T), s2 = detail::csqr(s1), s3 = detail::cmul(s2, s1), s4 = detail::csqr(s2);
-        float2 bq = W(n1 * t);
+        const unsigned kfix = slab % (unsigned)a.kdiv;
+        const float2 s1 = W(cidx * (unsigned)(a.kscale * T)), s2 = detail::csqr(s1), s3 = detail::cmul(s2, s1), s4 = detail::csqr(s2);
+        float2 bq = W(cidx * (kfix + (unsigned)a.kscale * t));
 #pragma unroll
         for (int q = 0; q < R / 4; q++) {
             v[4 * q] = detail::cmul(v[4 * q], bq);
@@ -129,7 +154,7 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < NBOX; b++) plat::tma_store_2d(&a.out_map, 32 * g, row0 + b * BOX_ROWS, tile + b * BOX_ROWS * 16);
+        for (int b = 0; b < NBOX; b++) plat::tma_store_2d(&a.out_map, out_c0, out_row0 + b * BOX_ROWS, tile + b * BOX_ROWS * 16);
         plat::bulk_commit();
         plat::bulk_wait_read0();  // the tile must outlive the store's reads
     }
@@ -159,6 +184,7 @@ PassInfo pass_info(int dir, int pass)
 PassInfo pass_for(int log2len, int dir, int pass)
 {
     switch (log2len) {
+        case 6: return pass_info<6>(dir, pass);
         case 7: return pass_info<7>(dir, pass);
         case 8: return pass_info<8>(dir, pass);
         default: return pass_info<9>(dir, pass);
@@ -167,7 +193,7 @@ PassInfo pass_for(int log2len, int dir, int pass)
 
 struct DevState {
     std::mutex mu;
-    float2* wt[kMaxLog2 + 1] = {};
+    float2* wt[kMaxLog2 + 1] = {};  // three-level twiddle tables by log2 of the modulus
     cudaMemPool_t pool = nullptr;
     std::vector<const void*> attr_done;
 };
@@ -184,49 +210,72 @@ int failf(char* err, int cap, int* cuda, int code, const char* fmt, const char* 
     do {                                                                                                         \
         cudaError_t e__ = (expr);                                                                                \
         if (e__ != cudaSuccess)                                                                                  \
-            return failf(err, errcap, cuda, e__ == cudaErrorMemoryAllocation ? 2 : 1, "smfft (two-pass transform): " #expr ": %s", cudaGetErrorString(e__)); \
+            return failf(err, errcap, cuda, e__ == cudaErrorMemoryAllocation ? 2 : 1, "smfft (multi-pass transform): " #expr ": %s", cudaGetErrorString(e__)); \
     } while (0)
+
+// W_M^j (j < 512), W_M^(512 j), W_M^(2^18 j), forward sign, rounded from FP64: W_M^p = lo[p & 511] mid[(p >> 9) & 511] hi[p >> 18]
+int twiddle_table(DevState& st, int log2m, float2** out, char* err, int errcap, int* cuda)
+{
+    if (!st.wt[log2m]) {
+        const long long M = 1LL << log2m;
+        std::vector<float2> h(1536);
+        for (int lvl = 0; lvl < 3; lvl++)
+            for (long long j = 0; j < 512; j++) {
+                const long long p = (j << (lvl == 0 ? 0 : lvl == 1 ? 9 : 18)) % M;
+                const double ang = -2.0 * M_PI * (double)p / (double)M;
+                h[lvl * 512 + j] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        float2* d = nullptr;
+        BIG_TRY(cudaMalloc((void**)&d, sizeof(float2) * h.size()));
+        cudaError_t e = cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return failf(err, errcap, cuda, 1, "smfft: twiddle table upload failed: %s", cudaGetErrorString(e));
+        }
+        st.wt[log2m] = d;
+    }
+    *out = st.wt[log2m];
+    return 0;
+}
 
 }  // namespace
 
-// the factorisation: N2 = length of pass A (strided), N1 = length of pass B (contiguous)
-static void split(int e, int* log2_n2, int* log2_n1)
+// The factorisation.  Two passes (2^15 .. 2^18): N = N1 N2, lengths (N2 strided, N1 contiguous).  Three passes (2^19 .. 2^24):
+// N = N1 N2 N3, n = n1 + N1 n2 + N1 N2 n3, k = k3 + N3 k2 + N2 N3 k1:
+//   pass 1: over n3 (stride N1 N2), times W_(N2 N3)^(n2 k3);  pass 2: over n2 (stride N1), times W_N^(n1 (k3 + N3 k2));
+//   pass 3: over n1 (contiguous), written to X[k3 + N3 k2 + N2 N3 k1] -- a tile gathers 16 consecutive k3.
+// All three-pass lengths are 64 .. 256 points (32 KB tiles at most).
+static void split(int e, int* l3, int* l2, int* l1)
 {
-    *log2_n2 = e == 18 ? 9 : e == 17 ? SMFFT_BIG_SPLIT17 : 8;
-    *log2_n1 = e - *log2_n2;
+    if (e <= 18) {
+        *l3 = 0;
+        *l2 = e == 18 ? 9 : e == 17 ? SMFFT_BIG_SPLIT17 : 8;
+        *l1 = e - *l2;
+    } else {
+        *l1 = (e + 2) / 3;
+        *l2 = (e - *l1 + 1) / 2;
+        *l3 = e - *l1 - *l2;
+    }
 }
 
 int exec(const Params& p, long long* launches, char* err, int errcap, int* cuda)
 {
-    if (p.e < kMinLog2 || p.e > kMaxLog2) return failf(err, errcap, cuda, 0, "smfft: two-pass transforms cover 2^15 .. 2^18 points%s", "");
+    if (p.e < kMinLog2 || p.e > kMaxLog2) return failf(err, errcap, cuda, 0, "smfft: multi-pass transforms cover 2^15 .. 2^24 points%s", "");
     if (p.n_ffts <= 0) return 0;
     int dev = -1;
     BIG_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return failf(err, errcap, cuda, 0, "smfft: device ordinal out of range%s", "");
     DevState& st = g_state[dev];
-    int l2, l1;
-    split(p.e, &l2, &l1);
-    const long long N = 1LL << p.e, N1 = 1LL << l1, N2 = 1LL << l2;
-    const PassInfo pa = pass_for(l2, p.dir, 0), pb = pass_for(l1, p.dir, 1);
+    int l3, l2, l1;
+    split(p.e, &l3, &l2, &l1);
+    const bool three = l3 > 0;
+    const long long N = 1LL << p.e, N1 = 1LL << l1, N2 = 1LL << l2, N3 = 1LL << l3;
+    const PassInfo k1 = pass_for(three ? l3 : l2, p.dir, 0), k2 = pass_for(l2, p.dir, 0), k3 = pass_for(l1, p.dir, 1);
+    float2 *wt_n = nullptr, *wt_23 = nullptr;
     {
         std::lock_guard<std::mutex> lk(st.mu);
-        if (!st.wt[p.e]) {
-            // W_N^j for j < 512 and W_N^(512 j) for j < N / 512 (<= 512), forward sign, rounded from FP64
-            std::vector<float2> h(1024, make_float2(1.0f, 0.0f));
-            for (int j = 0; j < 512; j++) {
-                const double a0 = -2.0 * M_PI * (double)j / (double)N, a1 = -2.0 * M_PI * (double)j * 512.0 / (double)N;
-                h[j] = make_float2((float)cos(a0), (float)sin(a0));
-                if (j < N / 512) h[512 + j] = make_float2((float)cos(a1), (float)sin(a1));
-            }
-            float2* d = nullptr;
-            BIG_TRY(cudaMalloc((void**)&d, sizeof(float2) * 1024));
-            cudaError_t e = cudaMemcpy(d, h.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) {
-                cudaFree(d);
-                return failf(err, errcap, cuda, 1, "smfft: twiddle table upload failed: %s", cudaGetErrorString(e));
-            }
-            st.wt[p.e] = d;
-        }
+        if (twiddle_table(st, p.e, &wt_n, err, errcap, cuda)) return 1;
+        if (three && twiddle_table(st, l2 + l3, &wt_23, err, errcap, cuda)) return 1;
         if (!st.pool) {
             cudaMemPoolProps props;
             memset(&props, 0, sizeof(props));
@@ -237,7 +286,7 @@ int exec(const Params& p, long long* launches, char* err, int errcap, int* cuda)
             unsigned long long keep = ~0ULL;  // the scratch of one call serves the next: nothing goes back to the driver until release()
             BIG_TRY(cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &keep));
         }
-        for (const PassInfo* k : {&pa, &pb}) {
+        for (const PassInfo* k : {&k1, &k2, &k3}) {
             bool need = true;
             for (const void* f : st.attr_done) need &= (f != (const void*)k->fn);
             if (need) {
@@ -254,37 +303,58 @@ int exec(const Params& p, long long* launches, char* err, int errcap, int* cuda)
     float2* scratch = nullptr;
     BIG_TRY(cudaMallocFromPoolAsync((void**)&scratch, (size_t)(chunk * fft_bytes), st.pool, p.stream));  // stream-ordered: safe across host threads and streams
     int rc = 0;
+    auto launch = [&](const PassInfo& k, PassArgs& a, long long tiles, const char* what) {
+        void* params[] = {&a};
+        cudaError_t e = cudaLaunchKernel((const void*)k.fn, dim3((unsigned)tiles), dim3((unsigned)k.threads), params, (size_t)k.smem, p.stream);
+        if (e != cudaSuccess) return failf(err, errcap, cuda, 1, "smfft: multi-pass transform, kernel launch: %s", cudaGetErrorString(e));
+        (void)what;
+        if (launches) *launches += 1;
+        return 0;
+    };
+    auto box = [](long long len) { return len > 256 ? 256 : (int)len; };
     for (long long f0 = 0; f0 < p.n_ffts && !rc; f0 += chunk) {
         const long long cf = p.n_ffts - f0 < chunk ? p.n_ffts - f0 : chunk;
         const float2* in = (const float2*)p.in + f0 * N;
         float2* out = (float2*)p.out + f0 * N;
         PassArgs a;
+        int bad = 0;
+        if (three) {
+            // pass 1: x -> scratch, columns of the [N3 cf rows][N1 N2 points] matrix
+            memset(&a, 0, sizeof(a));
+            a.base_tw = (const float2*)p.base_tw;
+            a.wt = wt_23;
+            bad |= host::encode_strided_map(&a.in_map, in, 2 * N1 * N2, N3 * cf, box(N3));
+            bad |= host::encode_strided_map(&a.out_map, scratch, 2 * N1 * N2, N3 * cf, box(N3));
+            a.groups = (int)(N1 * N2 / 16);
+            a.col_shift = l1;  // column n1 + N1 n2 -> n2
+            a.kdiv = 1;
+            a.kscale = 1;
+            if (bad) { rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (multi-pass transform, pass 1)%s", ""); break; }
+            if ((rc = launch(k1, a, cf * a.groups, "pass 1"))) break;
+        }
+        // column pass over n2: two passes: x -> scratch; three passes: scratch -> scratch in place (a tile reads and writes the same box)
         memset(&a, 0, sizeof(a));
         a.base_tw = (const float2*)p.base_tw;
-        a.wt = st.wt[p.e];
-        // pass A: x -> scratch
-        int r0 = host::encode_strided_map(&a.in_map, in, 2 * N1, N2 * cf, N2 > 256 ? 256 : (int)N2);
-        int r1 = host::encode_strided_map(&a.out_map, scratch, 2 * N1, N2 * cf, N2 > 256 ? 256 : (int)N2);
-        if (r0 || r1) { rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (two-pass transform, pass A)%s", ""); break; }
+        a.wt = wt_n;
+        bad |= host::encode_strided_map(&a.in_map, three ? (const void*)scratch : (const void*)in, 2 * N1, N2 * N3 * cf, box(N2));
+        bad |= host::encode_strided_map(&a.out_map, scratch, 2 * N1, N2 * N3 * cf, box(N2));
         a.groups = (int)(N1 / 16);
-        void* params[] = {&a};
-        cudaError_t e = cudaLaunchKernel((const void*)pa.fn, dim3((unsigned)(cf * a.groups)), dim3((unsigned)pa.threads), params, (size_t)pa.smem, p.stream);
-        if (e != cudaSuccess) { rc = failf(err, errcap, cuda, 1, "smfft: two-pass transform, pass A launch: %s", cudaGetErrorString(e)); break; }
-        // pass B: scratch -> X
-        PassArgs b;
-        memset(&b, 0, sizeof(b));
-        b.base_tw = (const float2*)p.base_tw;
-        if (host::encode_tile_map(&b.in_map, scratch, cf * N / 16, N1 > 256 ? 256 : (int)N1)) {
-            rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (two-pass transform, pass B input)%s", "");
-            break;
-        }
-        r1 = host::encode_strided_map(&b.out_map, out, 2 * N2, N1 * cf, N1 > 256 ? 256 : (int)N1);
-        if (r1) { rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (two-pass transform, pass B)%s", ""); break; }
-        b.groups = (int)(N2 / 16);
-        void* params_b[] = {&b};
-        e = cudaLaunchKernel((const void*)pb.fn, dim3((unsigned)(cf * b.groups)), dim3((unsigned)pb.threads), params_b, (size_t)pb.smem, p.stream);
-        if (e != cudaSuccess) { rc = failf(err, errcap, cuda, 1, "smfft: two-pass transform, pass B launch: %s", cudaGetErrorString(e)); break; }
-        if (launches) *launches += 2;
+        a.col_shift = 0;
+        a.kdiv = (int)N3;    // slab = fft N3 + k3
+        a.kscale = (int)N3;  // W_N^(n1 (k3 + N3 k2))
+        if (bad) { rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (multi-pass transform, column pass)%s", ""); break; }
+        if ((rc = launch(k2, a, cf * N3 * a.groups, "column pass"))) break;
+        // row pass over n1: scratch -> X
+        memset(&a, 0, sizeof(a));
+        a.base_tw = (const float2*)p.base_tw;
+        bad |= host::encode_tile_map(&a.in_map, scratch, cf * N / 16, three ? (int)(N1 / 16) : box(N1));
+        bad |= host::encode_strided_map(&a.out_map, out, 2 * N2 * N3, N1 * cf, box(N1));
+        a.groups = (int)((three ? N3 : N2) / 16);
+        a.nmid = three ? (int)N2 : 1;
+        a.out_col_scale = (int)N3;  // X[k3 + N3 k2 + N2 N3 k1]: the box of (k2, 16 k3) starts at column N3 k2 + 16 g
+        a.kdiv = 1;
+        if (bad) { rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (multi-pass transform, row pass)%s", ""); break; }
+        if ((rc = launch(k3, a, cf * a.nmid * a.groups, "row pass"))) break;
     }
     cudaError_t e = cudaFreeAsync(scratch, p.stream);
     if (!rc && e != cudaSuccess) rc = failf(err, errcap, cuda, 1, "smfft: cudaFreeAsync: %s", cudaGetErrorString(e));

@@ -1,11 +1,11 @@
-// big_fft.hpp -- C2C transforms of 2^15 .. 2^18 points in two passes (host interface of big_fft.cu).
+// big_fft.hpp -- C2C transforms of 2^15 .. 2^24 points in two or three passes over HBM (host interface of big_fft.cu).
 #pragma once
 #include <cuda_runtime.h>
 
 namespace smfft {
 namespace big {
 
-constexpr int kMinLog2 = 15, kMaxLog2 = 18;
+constexpr int kMinLog2 = 15, kMaxLog2 = 24;  // two passes up to 2^18 points, three from 2^19
 
 struct Params {
     int e;                 // log2 of the transform length, kMinLog2 .. kMaxLog2

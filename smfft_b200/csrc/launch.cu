@@ -325,7 +325,7 @@ static int launch_batch(int mode, int e, int dir, int reorder, int reps, const v
     if (n_points <= 0) return 0;
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail("smfft: device pointers must be 16-byte aligned");
     if (e >= big::kMinLog2) {
-        // 2^15 .. 2^18 points: two passes over HBM (big_fft.cu), natural order, C2C
+        // 2^15 .. 2^24 points: two or three passes over HBM (big_fft.cu), natural order, C2C
         big::Params bp{e, dir, d_in, d_out, n_points >> e, stream, ds->tw, (long long)g_big_chunk_mib.load() << 20};
         long long launched = 0;
         int cuda = 0;
@@ -399,8 +399,8 @@ static int c2c_call(Call* c, const void* d_in, void* d_out, int fft_size, long l
 {
     const int e = ilog2_exact(fft_size);
     if (e < 5 || e > big::kMaxLog2 || (e >= 13 && reps > 1))
-        return fail("smfft: wrong FFT length %d (C2C supports 32..262144, FFT_multiple 32..4096)", fft_size);
-    if (e >= big::kMinLog2 && !reorder) return fail("smfft: transforms of %d points (two passes) run in natural order only (reorder = 1)", fft_size);
+        return fail("smfft: wrong FFT length %d (C2C supports 32..16777216, FFT_multiple 32..4096)", fft_size);
+    if (e >= big::kMinLog2 && !reorder) return fail("smfft: transforms of %d points (several passes over HBM) run in natural order only (reorder = 1)", fft_size);
     if (n_ffts < 0) return fail("smfft: negative nFFTs");
     int dir = inverse ? 1 : 0;
     if (g_opt_quirk4096.load() && fft_size == 4096 && inverse && !reorder) dir = 0;  // CT/SM_FFT_parameters.cuh:388

@@ -44,8 +44,8 @@ def test_argument_errors_do_not_need_a_device(lib):
     ms = ctypes.c_double(0)
     assert lib.smfft_external_benchmark(None, None, 48, 10, 0, 1, ctypes.byref(ms)) != 0
     assert b"wrong FFT length" in lib.smfft_last_error()          # CT:656-658 prints the same words
-    assert lib.smfft_external_benchmark(None, None, 1 << 19, 10, 0, 1, ctypes.byref(ms)) != 0
-    assert b"wrong FFT length" in lib.smfft_last_error()          # two-pass transforms stop at 2^18 points
+    assert lib.smfft_external_benchmark(None, None, 1 << 25, 10, 0, 1, ctypes.byref(ms)) != 0
+    assert b"wrong FFT length" in lib.smfft_last_error()          # multi-pass transforms stop at 2^24 points
     assert lib.smfft_external_benchmark(None, None, 1 << 15, 10, 0, 0, ctypes.byref(ms)) != 0
     assert b"natural order" in lib.smfft_last_error()             # ... and take natural-order input only
     assert lib.smfft_multiple_benchmark(None, None, 1 << 15, 200, 0, 1, ctypes.byref(ms)) != 0

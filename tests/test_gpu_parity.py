@@ -739,7 +739,7 @@ def test_c2c_beyond_the_reference(sm, n, io, tw):
     with pytest.raises(sm.SmfftError):
         sm.FFT_multiple_benchmark(d, d, n, 200, False, True)      # the repeated benchmark stops at 4096 points
     with pytest.raises(sm.SmfftError):
-        sm.exec_c2c(d, d, 1 << 19, 1, False, True)              # two-pass transforms stop at 2^18 points
+        sm.exec_c2c(d, d, 1 << 25, 1, False, True)              # multi-pass transforms stop at 2^24 points
     sm.set_option("io", 0)
     sm.set_option("twiddle", 0)
 
@@ -802,28 +802,30 @@ def test_randomized_configurations(sm, seed):
         sm.set_option("two_pass_chunk_mib", 1024)
 
 
-@pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 17, 1 << 18])
+@pytest.mark.parametrize("n", [1 << e for e in range(15, 25)])
 def test_two_pass_transforms(sm, n):
-    """2^15 .. 2^18 points (beyond the reference, SURVEY.md 8f-4 "N > 4096 via multi-pass"): N = N1 N2 in two passes over HBM
-    (csrc/big_fft.cu), strided TMA boxes, twiddles from a two-level FP64-rounded table.  Both directions against the FP64 DFT;
-    batches of 1, 5 and 37; chunked (scratch smaller than the batch); in place; the host-timed entry point; error contract."""
+    """2^15 .. 2^24 points (beyond the reference, SURVEY.md 8f-4 "N > 4096 via multi-pass"): N = N1 N2 in two passes over HBM up
+    to 2^18 points, N = N1 N2 N3 in three from 2^19 (csrc/big_fft.cu), strided TMA boxes, twiddles from a three-level
+    FP64-rounded table.  Both directions against the FP64 DFT; batches of 1, 5 and 37 (fewer for the largest sizes); chunked
+    (scratch smaller than the batch); in place; the host-timed entry point; error contract."""
     try:
-        for nf in (1, 5, 37):
+        for nf in ((1, 5, 37) if n <= (1 << 18) else (1, 3) if n <= (1 << 22) else (2,)):
             x = O.uniform_c64(nf, n, seed=n % 1000 + nf)
             for inverse in (False, True):
                 assert O.rel_l2(run_c2c(sm, x, inverse, True), O.ct_c2c_fp64(x, inverse, True)) < TOL, (n, nf, inverse)
-        x = O.uniform_c64(11, n, seed=3)
+        nb = 11 if n <= (1 << 18) else 3
+        x = O.uniform_c64(nb, n, seed=3)
         want = O.ct_c2c_fp64(x, False, True)
-        sm.set_option("two_pass_chunk_mib", 1)                       # 1 MiB of scratch: 11 transforms in several chunks
+        sm.set_option("two_pass_chunk_mib", 1)                       # 1 MiB of scratch: one transform (or a few) per chunk
         assert O.rel_l2(run_c2c(sm, x, False, True), want) < TOL
         d = to_dev(x)
-        sm.exec_c2c(d, d, n, 11, False, True)                         # in place, chunked
+        sm.exec_c2c(d, d, n, nb, False, True)                         # in place, chunked
         torch.cuda.synchronize()
         assert O.rel_l2(c64(d), want) < TOL
         sm.set_option("two_pass_chunk_mib", 1024)
         d = to_dev(x)
         out = torch.zeros_like(d)
-        assert sm.FFT_external_benchmark(d, out, n, 11, False, True) > 0
+        assert sm.FFT_external_benchmark(d, out, n, nb, False, True) > 0
         torch.cuda.synchronize()
         assert O.rel_l2(c64(out), want) < TOL
         assert np.array_equal(c64(d), x)                              # the input is left alone
@@ -835,7 +837,7 @@ def test_two_pass_transforms(sm, n):
         k = np.arange(n)
         assert np.max(np.abs(y - np.exp(-2j * np.pi * ((p * k) % n) / n))) < 1e-5
         with pytest.raises(sm.SmfftError, match="natural order"):
-            sm.exec_c2c(d, out, n, 11, False, False)                  # no bit-reversed-input flavour for two-pass sizes
+            sm.exec_c2c(d, out, n, nb, False, False)                  # no bit-reversed-input flavour for multi-pass sizes
         with pytest.raises(sm.SmfftError):
             sm.FFT_multiple_benchmark(d, out, n, 200, False, True)
     finally:

@@ -1,7 +1,8 @@
-"""CPU model of the two-pass (four-step) factorisation that smfft_b200/csrc/big_fft.cu runs for 2^15 .. 2^18 points: the same index
-conventions (n = n1 + N1 n2, k = N2 k1 + k2), the same split of the sizes, the same two-level FP64-rounded twiddle table
-(W_N^j for j < 512 and W_N^(512 j)) evaluated in float32 -- against numpy's FP64 FFT.  Pins the algebra and the table layout
-without a GPU; the kernels themselves are checked by tests/test_gpu_parity.py::test_two_pass_transforms."""
+"""CPU model of the multi-pass factorisations that smfft_b200/csrc/big_fft.cu runs: two passes for 2^15 .. 2^18 points
+(n = n1 + N1 n2, k = N2 k1 + k2), three for 2^19 .. 2^24 (n = n1 + N1 n2 + N1 N2 n3, k = k3 + N3 k2 + N2 N3 k1) -- the same index
+conventions, the same split of the sizes, the same three-level FP64-rounded twiddle table (W_M^j, W_M^(512 j), W_M^(2^18 j))
+evaluated in float32 -- against numpy's FP64 FFT.  Pins the algebra and the table layout without a GPU; the kernels
+themselves are checked by tests/test_gpu_parity.py::test_two_pass_transforms."""
 import numpy as np
 import pytest
 
@@ -51,7 +52,47 @@ def test_factorisation_and_twiddle_table(e, inverse):
     assert rel < 1e-6, rel
 
 
+def split3(e):
+    """log2 of (N3, N2, N1) for the three-pass sizes, as big_fft.cu"""
+    l1 = (e + 2) // 3
+    l2 = (e - l1 + 1) // 2
+    return e - l1 - l2, l2, l1
+
+
+def three_level(m, p):
+    """W_M^p = lo[p & 511] mid[(p >> 9) & 511] hi[p >> 18], every table entry rounded from FP64 to float32"""
+    j = np.arange(512, dtype=np.int64)
+    tab = [np.exp(-2j * np.pi * ((j << sh) % m) / m).astype(np.complex64) for sh in (0, 9, 18)]
+    return (tab[0][p & 511] * tab[1][(p >> 9) & 511]).astype(np.complex64) * tab[2][p >> 18]
+
+
+@pytest.mark.parametrize("e", [19, 20, 22])
+def test_three_pass_factorisation(e):
+    n = 1 << e
+    l3, l2, l1 = split3(e)
+    n3, n2, n1 = 1 << l3, 1 << l2, 1 << l1
+    assert l1 + l2 + l3 == e and all(6 <= v <= 8 for v in (l1, l2, l3))
+    rng = np.random.default_rng(e)
+    x = rng.random((1, n, 2), dtype=np.float32).view(np.complex64).reshape(1, n)
+    a = x.reshape(1, n3, n2, n1)                                              # [fft][n3][n2][n1]
+    a = np.fft.fft(a, axis=1).astype(np.complex64)                            # pass 1: over n3 -> [k3][n2][n1]
+    k3 = np.arange(n3, dtype=np.int64)[:, None, None]
+    i2 = np.arange(n2, dtype=np.int64)[None, :, None]
+    i1 = np.arange(n1, dtype=np.int64)[None, None, :]
+    a = a * three_level(n2 * n3, (i2 * k3) + 0 * i1)[None]                    # W_(N2 N3)^(n2 k3)
+    a = np.fft.fft(a, axis=2).astype(np.complex64)                            # pass 2: over n2 -> [k3][k2][n1]
+    p = i1 * (k3 + n3 * i2)                                                   # n1 (k3 + N3 k2) < N
+    assert p.max() < n
+    a = a * three_level(n, p)[None]
+    a = np.fft.fft(a, axis=3).astype(np.complex64)                            # pass 3: over n1 -> [k3][k2][k1]
+    got = np.transpose(a, (0, 3, 2, 1)).reshape(1, n)                         # X[k3 + N3 k2 + N2 N3 k1]
+    want = np.fft.fft(x.astype(np.complex128), axis=-1)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-6
+
+
 def test_split_covers_the_range():
+    for e in range(19, 25):
+        assert sum(split3(e)) == e and all(6 <= v <= 8 for v in split3(e))  # block transforms of 64 .. 256 points
     for e in range(15, 19):
         l2, l1 = split(e)
         assert l1 + l2 == e and 7 <= l1 <= 9 and 8 <= l2 <= 9     # block transforms of 128 .. 512 points, 16 per tile

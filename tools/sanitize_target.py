@@ -78,11 +78,11 @@ for n, nf in ((8192, 3 * 148 + 7), (16384, 2 * 148 + 9)):
         run(n, nf, False, True)
         run(n, nf, True, False)
 sm.set_option("io", 0)
-# two-pass transforms (2^15 .. 2^18 points): strided TMA boxes in and out, chunked scratch
+# multi-pass transforms (2^15 .. 2^24 points): strided TMA boxes in and out, chunked scratch
 sm.set_option("two_pass_chunk_mib", 2)
-for e in (15, 16, 17, 18):
-    run(1 << e, 3, False, True)
-    run(1 << e, 2, True, True)
+for e in (15, 16, 17, 18, 19, 20, 21):   # 19 and up: three passes, the last one gathering its 16 transforms box by box
+    run(1 << e, 3 if e <= 18 else 2, False, True)
+    run(1 << e, 2 if e <= 18 else 1, True, True)
 sm.set_option("two_pass_chunk_mib", 1024)
 lib = ctypes.CDLL(build_compat())
 P, I = ctypes.c_void_p, ctypes.c_int
