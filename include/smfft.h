@@ -50,7 +50,7 @@ extern "C" {
 int smfft_init(void);
 
 /* ---- Cooley-Tukey C2C: N = 32..4096 (the reference's range), 8192 / 16384 (beyond it, external only) and
- * 2^15 .. 2^18 (two passes over HBM with a library-owned, stream-ordered scratch of min(batch, "two_pass_chunk_mib");
+ * 2^15 .. 2^24 (two passes over HBM up to 2^18, three above, with a library-owned, stream-ordered scratch of min(batch, "two_pass_chunk_mib");
  * natural order only, in place allowed; smfft_pipeline_release() returns the scratch pool to the driver) -----
  * replaces int FFT_external_benchmark(float2*, float2*, int FFT_size, int nFFTs, bool inverse,
  *                                     bool reorder, double* FFT_time)                  CT:583-664
@@ -70,7 +70,7 @@ int smfft_exec_c2c(const void* d_in, void* d_out, int fft_size, long long n_ffts
 int smfft_exec_c2c_stream(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reorder,
                           void* stream);
 
-/* ---- Stockham C2C: N = 32..262144, natural order -----------------------------------------------
+/* ---- Stockham C2C: N = 32..2^24, natural order -------------------------------------------------
  * replaces void FFT_external_benchmark(float2*, float2*, int, int, double*)            ST:306-345
  *          void FFT_multiple_benchmark(float2*, float2*, int, int, double*)            ST:348-384
  * The reference's Stockham C2C directory is inverse-only; `inverse` selects the
@@ -129,7 +129,7 @@ int smfft_pipeline_release(void);
  * device from then on; smfft_select_report() lists the decisions, "select_reset" forgets them), "twiddle" (0 = table+powers
  * [default], 1 = MUFU __sincosf), "quirk_4096" (1 = reproduce FFT_4096_inverse_noreorder running
  * the forward transform, CT/SM_FFT_parameters.cuh:388; default 0 = mathematically correct),
- * "ctas_per_sm" (0 = built-in), "pipeline_chunk_mib" (default chunk of smfft_pipeline_host, 1..1024, default 128), "two_pass_chunk_mib" (batch chunk = scratch size of the 2^15..2^18-point transforms, 1..65536, default 1024), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
+ * "ctas_per_sm" (0 = built-in), "pipeline_chunk_mib" (default chunk of smfft_pipeline_host, 1..1024, default 128), "two_pass_chunk_mib" (batch chunk = scratch size of the multi-pass transforms, 2^15 points and up, 1..65536, default 1024), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
  * of shared memory), "device_sms" (read-only). */
 int smfft_set_option(const char* key, int value);
 int smfft_get_option(const char* key);

@@ -1,4 +1,4 @@
-// big_fft.cu -- C2C transforms of 2^15 .. 2^18 points: two passes over HBM (the "four-step" factorisation).
+// big_fft.cu -- C2C transforms of 2^15 .. 2^24 points: two passes over HBM (the "four-step" factorisation), three from 2^19.
 //
 // Beyond the reference ("N > 4096 via multi-pass"): KAdamek/SMFFT stops where one transform stops fitting one
 // CTA's shared memory.  N = N1 * N2, n = n1 + N1 n2, k = N2 k1 + k2:
