@@ -746,13 +746,13 @@ def test_c2c_beyond_the_reference(sm, n, io, tw):
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
 def test_randomized_configurations(sm, seed):
-    """Seeded sweep over what a caller can combine: size (32..262144), batch count (odd, prime, one, many tiles per CTA), staging
+    """Seeded sweep over what a caller can combine: size (32..4194304), batch count (odd, prime, one, many tiles per CTA), staging
     (io 0..5), twiddle source, direction, order, in place or not, first-use selection on or off -- C2C against the FP64 DFT, and
     R2C / C2R (64..8192 reals) against the packed FP64 forms.  A mismatch names the configuration."""
     rng = np.random.default_rng(seed)
     try:
         for it in range(60):
-            n = 1 << int(rng.integers(5, 19))                       # 32 .. 262144 (two passes from 32768 up)
+            n = 1 << int(rng.integers(5, 23))                       # 32 .. 4194304 (two passes from 32768 up, three from 524288)
             nf = int(rng.choice([1, 2, 3, 7, 31, 127, 149, 331, 1021])) if n >= 2048 else int(rng.choice([1, 3, 17, 257, 1031, 4099]))
             nf = max(1, min(nf, (1 << 22) // n))
             io, tw = int(rng.integers(0, 6)), int(rng.integers(0, 2))
