@@ -1,4 +1,4 @@
-// big_fft.cu -- C2C transforms of 2^15 .. 2^24 points: two passes over HBM (the "four-step" factorisation), three from 2^19.
+// big_fft.cu -- C2C transforms of 2^15 .. 2^24 points: two passes over HBM (the "four-step" factorisation), three from 2^21.
 //
 // Beyond the reference ("N > 4096 via multi-pass"): KAdamek/SMFFT stops where one transform stops fitting one
 // CTA's shared memory.  N = N1 * N2, n = n1 + N1 n2, k = N2 k1 + k2:
@@ -63,14 +63,23 @@ struct PassArgs {
 
 // one tile = 16 transforms of 2^LOG2LEN points.  PASS 0 = column pass (strided box in, twiddle, same box out), 1 = row pass
 // (16 transforms in -- contiguous, or gathered one box each when nmid > 1 --, strided box out)
-template <int LOG2LEN, int DIR, int PASS>
-__global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2LEN <= 7 ? 8 : LOG2LEN == 8 ? 4 : 2)) big_pass_kernel(const __grid_constant__ PassArgs a)
+template <int LOG2LEN, int DIR, int PASS, int LOG2W>
+__global__ void __launch_bounds__(((1 << LOG2W) << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2LEN <= 7 ? 8 : LOG2LEN == 8 ? 4 : 2)) big_pass_kernel(const __grid_constant__ PassArgs a)
 {
-    using F = BlockFFT<LOG2LEN, DIR, 16, TW_LUT, log2r_for(LOG2LEN)>;  // 512 points: 32 per thread, so a transform keeps 16 lanes
-    using SW = detail::LayoutSW128;
-    constexpr int LEN = 1 << LOG2LEN, TILE = 16 * LEN, T = F::T, R = F::R;
-    constexpr int BOX_ROWS = LEN > 256 ? 256 : LEN, NBOX = LEN / BOX_ROWS;
-    static_assert(F::THREADS == 16 * T, "16 transforms per block");
+    // WD transforms per tile: 16 (one 128-byte line per box row), or 8 for 1024-point passes (64-byte segments, 64 KB tiles)
+    constexpr int WD = 1 << LOG2W;
+    using F = BlockFFT<LOG2LEN, DIR, WD, TW_LUT, log2r_for(LOG2LEN)>;  // 512 points and up: 32 per thread
+    using SW = detail::LayoutSW128;  // tiles that arrive as rows of 128 bytes (the row pass's input)
+    // strided boxes: rows of WD points.  16 points = 128 bytes: SWIZZLE_128B.  8 points = 64 bytes: SWIZZLE_64B (16-byte chunk
+    // index, bits 4-5 of the address, XOR bits 7-8), two box rows per 128-byte line
+    struct SW64 {
+        static __device__ __forceinline__ int phys(int x) { return x ^ (((x >> 4) & 3) << 1); }
+    };
+    using SWT = typename std::conditional<WD == 8, SW64, SW>::type;
+    constexpr int LEN = 1 << LOG2LEN, TILE = WD * LEN, T = F::T, R = F::R;
+    constexpr int BOX_ROWS = LEN > 256 ? 256 : LEN, NBOX = LEN / BOX_ROWS;            // strided boxes: LEN rows of WD points
+    constexpr int IN_ROWS = TILE / 16, IN_BOX = IN_ROWS > 256 ? 256 : IN_ROWS, IN_NBOX = IN_ROWS / IN_BOX;  // contiguous tile: rows of 128 bytes
+    static_assert(F::THREADS == WD * T, "WD transforms per block");
     extern __shared__ unsigned char raw[];
     unsigned char* smem = raw + ((1024u - (plat::smem_u32(raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs a 1 KB aligned tile
     float2* tile = reinterpret_cast<float2*>(smem);
@@ -82,11 +91,11 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
     const unsigned slab = id / (unsigned)a.groups;  // column pass: which LEN rows; row pass: fft * nmid + kmid
     int out_c0, out_row0;
     if constexpr (PASS == 0) {
-        out_c0 = 32 * g;
+        out_c0 = 2 * WD * g;
         out_row0 = (int)(slab * LEN);
     } else {
         const int kmid = (int)(slab % (unsigned)a.nmid);
-        out_c0 = 32 * g + 2 * a.out_col_scale * kmid;
+        out_c0 = 2 * WD * g + 2 * a.out_col_scale * kmid;
         out_row0 = (int)(slab / (unsigned)a.nmid) * LEN;
     }
 
@@ -100,15 +109,15 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
         plat::mbar_arrive_expect_tx(bar, TILE * 8);
         if constexpr (PASS == 0) {
 #pragma unroll
-            for (int b = 0; b < NBOX; b++) plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, out_c0, out_row0 + b * BOX_ROWS, bar);
+            for (int b = 0; b < NBOX; b++) plat::tma_load_2d(tile + b * BOX_ROWS * WD, &a.in_map, out_c0, out_row0 + b * BOX_ROWS, bar);
         } else if (a.nmid == 1) {
 #pragma unroll
-            for (int b = 0; b < NBOX; b++) plat::tma_load_2d(tile + b * BOX_ROWS * 16, &a.in_map, 0, (int)(id * (unsigned)LEN) + b * BOX_ROWS, bar);  // 16 contiguous transforms = LEN rows of 128 bytes
+            for (int b = 0; b < IN_NBOX; b++) plat::tma_load_2d(tile + b * IN_BOX * 16, &a.in_map, 0, (int)(id * (unsigned)IN_ROWS) + b * IN_BOX, bar);  // WD contiguous transforms = IN_ROWS rows of 128 bytes
         } else {
             // gathered: transform j of the tile is LEN / 16 rows of 128 bytes somewhere in the scratch, one box each
             const unsigned fft = slab / (unsigned)a.nmid, kmid = slab % (unsigned)a.nmid;
-            const long long tr0 = kmid + (long long)a.nmid * (16 * g + 16LL * a.groups * fft);
-            for (int j = 0; j < 16; j++) plat::tma_load_2d(tile + j * LEN, &a.in_map, 0, (int)((tr0 + (long long)a.nmid * j) * (LEN / 16)), bar);
+            const long long tr0 = kmid + (long long)a.nmid * (WD * g + (long long)WD * a.groups * fft);
+            for (int j = 0; j < WD; j++) plat::tma_load_2d(tile + j * LEN, &a.in_map, 0, (int)((tr0 + (long long)a.nmid * j) * (LEN / 16)), bar);
         }
     }
     F::fill_twiddles(stw, a.base_tw);
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
     plat::mbar_wait(bar, 0);
     if constexpr (PASS == 0) {
 #pragma unroll
-        for (int m = 0; m < R; m++) v[m] = tile[SW::phys((t + m * T) * 16 + f)];  // column f of the box
+        for (int m = 0; m < R; m++) v[m] = tile[SWT::phys((t + m * T) * WD + f)];  // column f of the box
     } else {
 #pragma unroll
         for (int m = 0; m < R; m++) v[m] = tile[SW::phys(F::index(m))];  // transform f of the tile: 16 lanes read one 128-byte row
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
     if constexpr (PASS == 0) {
         // W_M^(cidx (kfix + kscale k)), k = t + m T: an accurate base and an accurate step from the three-level table, the
         // powers four at a time (at most R/4 + 2 roundings deep)
-        const unsigned cidx = (unsigned)(16 * g + f) >> a.col_shift;
+        const unsigned cidx = (unsigned)(WD * g + f) >> a.col_shift;
         auto W = [&](unsigned p) {  // p < M <= 2^24
             float2 w = detail::cmul(__ldg(a.wt + (p & 511)), __ldg(a.wt + 512 + ((p >> 9) & 511)));
             w = detail::cmul(w, __ldg(a.wt + 1024 + (p >> 18)));
@@ -149,21 +158,24 @@ __global__ void __launch_bounds__((16 << (LOG2LEN - log2r_for(LOG2LEN))), (LOG2L
 
     __syncthreads();  // the last exchange has been read by every thread
 #pragma unroll
-    for (int m = 0; m < R; m++) tile[SW::phys((t + m * T) * 16 + f)] = v[m];
+    for (int m = 0; m < R; m++) tile[SWT::phys((t + m * T) * WD + f)] = v[m];
     plat::fence_proxy_async();  // generic-proxy writes -> TMA store (async proxy)
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < NBOX; b++) plat::tma_store_2d(&a.out_map, out_c0, out_row0 + b * BOX_ROWS, tile + b * BOX_ROWS * 16);
+        for (int b = 0; b < NBOX; b++) plat::tma_store_2d(&a.out_map, out_c0, out_row0 + b * BOX_ROWS, tile + b * BOX_ROWS * WD);
         plat::bulk_commit();
         plat::bulk_wait_read0();  // the tile must outlive the store's reads
     }
 }
 
+SMFFT_CX int log2w_for(int log2len) { return log2len >= 10 ? 3 : 4; }  // transforms per tile: 16, or 8 for 1024-point passes
+
 template <int LOG2LEN>
 constexpr int pass_smem_bytes()
 {
-    return 16 * (1 << LOG2LEN) * 8 + 64 + ((BlockFFT<LOG2LEN, 0, 16, TW_LUT, log2r_for(LOG2LEN)>::TWIDDLE_POINTS * 8 + 127) & ~127) + 1024;
+    return (1 << log2w_for(LOG2LEN)) * (1 << LOG2LEN) * 8 + 64 +
+           ((BlockFFT<LOG2LEN, 0, (1 << log2w_for(LOG2LEN)), TW_LUT, log2r_for(LOG2LEN)>::TWIDDLE_POINTS * 8 + 127) & ~127) + 1024;
 }
 
 typedef void (*PassFn)(const PassArgs);
@@ -171,14 +183,16 @@ typedef void (*PassFn)(const PassArgs);
 struct PassInfo {
     PassFn fn;
     int threads, smem;
+    int width;  // transforms per tile
 };
 
 template <int LOG2LEN>
 PassInfo pass_info(int dir, int pass)
 {
-    PassFn fn = dir ? (pass ? big_pass_kernel<LOG2LEN, 1, 1> : big_pass_kernel<LOG2LEN, 1, 0>)
-                    : (pass ? big_pass_kernel<LOG2LEN, 0, 1> : big_pass_kernel<LOG2LEN, 0, 0>);
-    return PassInfo{fn, 16 << (LOG2LEN - log2r_for(LOG2LEN)), pass_smem_bytes<LOG2LEN>()};
+    constexpr int LW = log2w_for(LOG2LEN);
+    PassFn fn = dir ? (pass ? big_pass_kernel<LOG2LEN, 1, 1, LW> : big_pass_kernel<LOG2LEN, 1, 0, LW>)
+                    : (pass ? big_pass_kernel<LOG2LEN, 0, 1, LW> : big_pass_kernel<LOG2LEN, 0, 0, LW>);
+    return PassInfo{fn, (1 << LW) << (LOG2LEN - log2r_for(LOG2LEN)), pass_smem_bytes<LOG2LEN>(), 1 << LW};
 }
 
 PassInfo pass_for(int log2len, int dir, int pass)
@@ -187,7 +201,8 @@ PassInfo pass_for(int log2len, int dir, int pass)
         case 6: return pass_info<6>(dir, pass);
         case 7: return pass_info<7>(dir, pass);
         case 8: return pass_info<8>(dir, pass);
-        default: return pass_info<9>(dir, pass);
+        case 9: return pass_info<9>(dir, pass);
+        default: return pass_info<10>(dir, pass);
     }
 }
 
@@ -240,16 +255,17 @@ int twiddle_table(DevState& st, int log2m, float2** out, char* err, int errcap, 
 
 }  // namespace
 
-// The factorisation.  Two passes (2^15 .. 2^18): N = N1 N2, lengths (N2 strided, N1 contiguous).  Three passes (2^19 .. 2^24):
+// The factorisation.  Two passes (2^15 .. 2^20): N = N1 N2, lengths (N2 strided, N1 contiguous).  Three passes (2^21 .. 2^24):
 // N = N1 N2 N3, n = n1 + N1 n2 + N1 N2 n3, k = k3 + N3 k2 + N2 N3 k1:
 //   pass 1: over n3 (stride N1 N2), times W_(N2 N3)^(n2 k3);  pass 2: over n2 (stride N1), times W_N^(n1 (k3 + N3 k2));
 //   pass 3: over n1 (contiguous), written to X[k3 + N3 k2 + N2 N3 k1] -- a tile gathers 16 consecutive k3.
 // All three-pass lengths are 64 .. 256 points (32 KB tiles at most).
 static void split(int e, int* l3, int* l2, int* l1)
 {
-    if (e <= 18) {
+    if (e <= 20) {
+        // two passes; 2^19 = 512 x 1024 and 2^20 = 1024 x 1024 run 1024-point passes on 8-transform tiles (64 KB)
         *l3 = 0;
-        *l2 = e == 18 ? 9 : e == 17 ? SMFFT_BIG_SPLIT17 : 8;
+        *l2 = e == 20 ? 10 : e >= 18 ? 9 : e == 17 ? SMFFT_BIG_SPLIT17 : 8;
         *l1 = e - *l2;
     } else {
         *l1 = (e + 2) / 3;
@@ -323,9 +339,9 @@ int exec(const Params& p, long long* launches, char* err, int errcap, int* cuda)
             memset(&a, 0, sizeof(a));
             a.base_tw = (const float2*)p.base_tw;
             a.wt = wt_23;
-            bad |= host::encode_strided_map(&a.in_map, in, 2 * N1 * N2, N3 * cf, box(N3));
-            bad |= host::encode_strided_map(&a.out_map, scratch, 2 * N1 * N2, N3 * cf, box(N3));
-            a.groups = (int)(N1 * N2 / 16);
+            bad |= host::encode_strided_map(&a.in_map, in, 2 * N1 * N2, N3 * cf, box(N3), 2 * k1.width);
+            bad |= host::encode_strided_map(&a.out_map, scratch, 2 * N1 * N2, N3 * cf, box(N3), 2 * k1.width);
+            a.groups = (int)(N1 * N2 / k1.width);
             a.col_shift = l1;  // column n1 + N1 n2 -> n2
             a.kdiv = 1;
             a.kscale = 1;
@@ -336,9 +352,9 @@ int exec(const Params& p, long long* launches, char* err, int errcap, int* cuda)
         memset(&a, 0, sizeof(a));
         a.base_tw = (const float2*)p.base_tw;
         a.wt = wt_n;
-        bad |= host::encode_strided_map(&a.in_map, three ? (const void*)scratch : (const void*)in, 2 * N1, N2 * N3 * cf, box(N2));
-        bad |= host::encode_strided_map(&a.out_map, scratch, 2 * N1, N2 * N3 * cf, box(N2));
-        a.groups = (int)(N1 / 16);
+        bad |= host::encode_strided_map(&a.in_map, three ? (const void*)scratch : (const void*)in, 2 * N1, N2 * N3 * cf, box(N2), 2 * k2.width);
+        bad |= host::encode_strided_map(&a.out_map, scratch, 2 * N1, N2 * N3 * cf, box(N2), 2 * k2.width);
+        a.groups = (int)(N1 / k2.width);
         a.col_shift = 0;
         a.kdiv = (int)N3;    // slab = fft N3 + k3
         a.kscale = (int)N3;  // W_N^(n1 (k3 + N3 k2))
@@ -347,11 +363,11 @@ int exec(const Params& p, long long* launches, char* err, int errcap, int* cuda)
         // row pass over n1: scratch -> X
         memset(&a, 0, sizeof(a));
         a.base_tw = (const float2*)p.base_tw;
-        bad |= host::encode_tile_map(&a.in_map, scratch, cf * N / 16, three ? (int)(N1 / 16) : box(N1));
-        bad |= host::encode_strided_map(&a.out_map, out, 2 * N2 * N3, N1 * cf, box(N1));
-        a.groups = (int)((three ? N3 : N2) / 16);
+        bad |= host::encode_tile_map(&a.in_map, scratch, cf * N / 16, three ? (int)(N1 / 16) : box(k3.width * N1 / 16));
+        bad |= host::encode_strided_map(&a.out_map, out, 2 * N2 * N3, N1 * cf, box(N1), 2 * k3.width);
+        a.groups = (int)((three ? N3 : N2) / k3.width);
         a.nmid = three ? (int)N2 : 1;
-        a.out_col_scale = (int)N3;  // X[k3 + N3 k2 + N2 N3 k1]: the box of (k2, 16 k3) starts at column N3 k2 + 16 g
+        a.out_col_scale = (int)N3;  // X[k3 + N3 k2 + N2 N3 k1]: the box of (k2, WD consecutive k3) starts at column N3 k2 + WD g
         a.kdiv = 1;
         if (bad) { rc = failf(err, errcap, cuda, 1, "smfft: cuTensorMapEncodeTiled failed (multi-pass transform, row pass)%s", ""); break; }
         if ((rc = launch(k3, a, cf * a.nmid * a.groups, "row pass"))) break;

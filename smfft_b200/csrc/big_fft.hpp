@@ -5,7 +5,7 @@
 namespace smfft {
 namespace big {
 
-constexpr int kMinLog2 = 15, kMaxLog2 = 24;  // two passes up to 2^18 points, three from 2^19
+constexpr int kMinLog2 = 15, kMaxLog2 = 24;  // two passes up to 2^20 points, three from 2^21
 
 struct Params {
     int e;                 // log2 of the transform length, kMinLog2 .. kMaxLog2

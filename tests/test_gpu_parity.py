@@ -752,7 +752,7 @@ def test_randomized_configurations(sm, seed):
     rng = np.random.default_rng(seed)
     try:
         for it in range(60):
-            n = 1 << int(rng.integers(5, 23))                       # 32 .. 4194304 (two passes from 32768 up, three from 524288)
+            n = 1 << int(rng.integers(5, 23))                       # 32 .. 4194304 (two passes from 32768 up, three from 2097152)
             nf = int(rng.choice([1, 2, 3, 7, 31, 127, 149, 331, 1021])) if n >= 2048 else int(rng.choice([1, 3, 17, 257, 1031, 4099]))
             nf = max(1, min(nf, (1 << 22) // n))
             io, tw = int(rng.integers(0, 6)), int(rng.integers(0, 2))
@@ -805,7 +805,7 @@ def test_randomized_configurations(sm, seed):
 @pytest.mark.parametrize("n", [1 << e for e in range(15, 25)])
 def test_two_pass_transforms(sm, n):
     """2^15 .. 2^24 points (beyond the reference, SURVEY.md 8f-4 "N > 4096 via multi-pass"): N = N1 N2 in two passes over HBM up
-    to 2^18 points, N = N1 N2 N3 in three from 2^19 (csrc/big_fft.cu), strided TMA boxes, twiddles from a three-level
+    to 2^20 points, N = N1 N2 N3 in three from 2^21 (csrc/big_fft.cu), strided TMA boxes, twiddles from a three-level
     FP64-rounded table.  Both directions against the FP64 DFT; batches of 1, 5 and 37 (fewer for the largest sizes); chunked
     (scratch smaller than the batch); in place; the host-timed entry point; error contract."""
     try:

@@ -1,5 +1,5 @@
-"""CPU model of the multi-pass factorisations that smfft_b200/csrc/big_fft.cu runs: two passes for 2^15 .. 2^18 points
-(n = n1 + N1 n2, k = N2 k1 + k2), three for 2^19 .. 2^24 (n = n1 + N1 n2 + N1 N2 n3, k = k3 + N3 k2 + N2 N3 k1) -- the same index
+"""CPU model of the multi-pass factorisations that smfft_b200/csrc/big_fft.cu runs: two passes for 2^15 .. 2^20 points
+(n = n1 + N1 n2, k = N2 k1 + k2), three for 2^21 .. 2^24 (n = n1 + N1 n2 + N1 N2 n3, k = k3 + N3 k2 + N2 N3 k1) -- the same index
 conventions, the same split of the sizes, the same three-level FP64-rounded twiddle table (W_M^j, W_M^(512 j), W_M^(2^18 j))
 evaluated in float32 -- against numpy's FP64 FFT.  Pins the algebra and the table layout without a GPU; the kernels
 themselves are checked by tests/test_gpu_parity.py::test_two_pass_transforms."""
@@ -8,18 +8,16 @@ import pytest
 
 
 def split(e):
-    """log2 of (N2 = strided pass A, N1 = contiguous pass B), as big_fft.cu"""
-    l2 = 9 if e == 18 else 8
+    """log2 of (N2 = strided pass A, N1 = contiguous pass B), as big_fft.cu: two passes up to 2^20 points"""
+    l2 = 10 if e == 20 else 9 if e >= 18 else 8
     return l2, e - l2
 
 
-def two_level_table(n):
-    j = np.arange(512)
-    lo = np.exp(-2j * np.pi * j / n).astype(np.complex64)
-    hi = np.ones(512, dtype=np.complex64)
-    m = n // 512
-    hi[:m] = np.exp(-2j * np.pi * j[:m] * 512.0 / n).astype(np.complex64)
-    return lo, hi
+def three_level(m, p):
+    """W_M^p = lo[p & 511] mid[(p >> 9) & 511] hi[p >> 18], every table entry rounded from FP64 to float32"""
+    j = np.arange(512, dtype=np.int64)
+    tab = [np.exp(-2j * np.pi * ((j << sh) % m) / m).astype(np.complex64) for sh in (0, 9, 18)]
+    return (tab[0][p & 511] * tab[1][(p >> 9) & 511]).astype(np.complex64) * tab[2][p >> 18]
 
 
 def two_pass(x, inverse):
@@ -27,12 +25,11 @@ def two_pass(x, inverse):
     e = n.bit_length() - 1
     l2, l1 = split(e)
     n2, n1 = 1 << l2, 1 << l1
-    lo, hi = two_level_table(n)
     a = x.reshape(-1, n2, n1)                                    # [fft][n2][n1]: n = n1 + N1 n2
     fa = (np.fft.ifft(a, axis=1) * n2 if inverse else np.fft.fft(a, axis=1)).astype(np.complex64)   # pass A: over n2 -> [fft][k2][n1]
-    p = np.arange(n2)[:, None] * np.arange(n1)[None, :]          # n1 k2 < N
-    assert p.max() < n and (p >> 9).max() < max(1, n // 512)
-    w = (lo[p & 511] * hi[p >> 9]).astype(np.complex64)          # the kernel's W(p) = lo[p & 511] * hi[p >> 9]
+    p = np.arange(n2, dtype=np.int64)[:, None] * np.arange(n1, dtype=np.int64)[None, :]          # n1 k2 < N
+    assert p.max() < n
+    w = three_level(n, p)                                        # the kernel's W(p)
     if inverse:
         w = np.conj(w)
     b = fa * w[None]
@@ -40,7 +37,7 @@ def two_pass(x, inverse):
     return np.transpose(fb, (0, 2, 1)).reshape(-1, n)            # X[N2 k1 + k2]: rows k1, columns k2
 
 
-@pytest.mark.parametrize("e", [15, 16, 17, 18])
+@pytest.mark.parametrize("e", [15, 16, 17, 18, 19, 20])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_factorisation_and_twiddle_table(e, inverse):
     n = 1 << e
@@ -59,14 +56,7 @@ def split3(e):
     return e - l1 - l2, l2, l1
 
 
-def three_level(m, p):
-    """W_M^p = lo[p & 511] mid[(p >> 9) & 511] hi[p >> 18], every table entry rounded from FP64 to float32"""
-    j = np.arange(512, dtype=np.int64)
-    tab = [np.exp(-2j * np.pi * ((j << sh) % m) / m).astype(np.complex64) for sh in (0, 9, 18)]
-    return (tab[0][p & 511] * tab[1][(p >> 9) & 511]).astype(np.complex64) * tab[2][p >> 18]
-
-
-@pytest.mark.parametrize("e", [19, 20, 22])
+@pytest.mark.parametrize("e", [21, 22, 23])
 def test_three_pass_factorisation(e):
     n = 1 << e
     l3, l2, l1 = split3(e)
@@ -91,9 +81,8 @@ def test_three_pass_factorisation(e):
 
 
 def test_split_covers_the_range():
-    for e in range(19, 25):
+    for e in range(21, 25):
         assert sum(split3(e)) == e and all(6 <= v <= 8 for v in split3(e))  # block transforms of 64 .. 256 points
-    for e in range(15, 19):
+    for e in range(15, 21):
         l2, l1 = split(e)
-        assert l1 + l2 == e and 7 <= l1 <= 9 and 8 <= l2 <= 9     # block transforms of 128 .. 512 points, 16 per tile
-        assert (1 << e) // 512 <= 512                              # the upper table has at most 512 entries
+        assert l1 + l2 == e and 7 <= l1 <= 10 and 8 <= l2 <= 10   # block transforms of 128 .. 1024 points (1024: 8 per tile, else 16)

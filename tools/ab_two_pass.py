@@ -32,6 +32,6 @@ for e in ([int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else (15
         best = min(best, ev[0].elapsed_time(ev[1]) / 10)
     ref = torch.fft.fft(torch.view_as_complex(x[:2]))
     err = (torch.view_as_complex(y[:2]) - ref).norm() / ref.norm()
-    out[str(n)] = {"ms": round(best, 4), "frac_of_floor": round((2 if e <= 18 else 3) * 1.313 / best, 3), "rel_l2_vs_torch": float(err)}
+    out[str(n)] = {"ms": round(best, 4), "frac_of_floor": round((2 if e <= 20 else 3) * 1.313 / best, 3), "rel_l2_vs_torch": float(err)}
     del x, y
 print(json.dumps(out))

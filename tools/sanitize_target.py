@@ -80,7 +80,7 @@ for n, nf in ((8192, 3 * 148 + 7), (16384, 2 * 148 + 9)):
 sm.set_option("io", 0)
 # multi-pass transforms (2^15 .. 2^24 points): strided TMA boxes in and out, chunked scratch
 sm.set_option("two_pass_chunk_mib", 2)
-for e in (15, 16, 17, 18, 19, 20, 21):   # 19 and up: three passes, the last one gathering its 16 transforms box by box
+for e in (15, 16, 17, 18, 19, 20, 21, 22):   # 19 / 20: 1024-point passes on 8-transform tiles; 21 and up: three passes, the last one gathering its 16 transforms box by box
     run(1 << e, 3 if e <= 18 else 2, False, True)
     run(1 << e, 2 if e <= 18 else 1, True, True)
 sm.set_option("two_pass_chunk_mib", 1024)
