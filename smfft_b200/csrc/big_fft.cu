@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(((1 << LOG2W) << (LOG2LEN - log2r_for(LOG2LEN)
     }
 }
 
-SMFFT_CX int log2w_for(int log2len) { return log2len >= 10 ? 3 : 4; }  // transforms per tile: 16, or 8 for 1024-point passes
+#ifndef SMFFT_BIG_W8_FROM
+#define SMFFT_BIG_W8_FROM 9  // 512-point passes too: 32 KB tiles, four CTAs per SM instead of two (2^17: 2.75 -> 2.64 ms, 2^18: 2.97 -> 2.78 ms)
+#endif
+SMFFT_CX int log2w_for(int log2len) { return log2len >= SMFFT_BIG_W8_FROM ? 3 : 4; }  // transforms per tile: 16, or 8 for 512- and 1024-point passes
 
 template <int LOG2LEN>
 constexpr int pass_smem_bytes()
