@@ -51,7 +51,8 @@ int smfft_init(void);
 
 /* ---- Cooley-Tukey C2C: N = 32..4096 (the reference's range), 8192 / 16384 (beyond it, external only) and
  * 2^15 .. 2^24 (two passes over HBM up to 2^20, three above, with a library-owned, stream-ordered scratch of min(batch, "two_pass_chunk_mib");
- * natural order only, in place allowed; smfft_pipeline_release() returns the scratch pool to the driver) -----
+ * natural order only, in place allowed; the "io", "twiddle" and "select" options do not apply to these sizes;
+ * smfft_pipeline_release() returns the scratch pool to the driver -- not while other calls run on that device) -----
  * replaces int FFT_external_benchmark(float2*, float2*, int FFT_size, int nFFTs, bool inverse,
  *                                     bool reorder, double* FFT_time)                  CT:583-664
  * reorder=1: natural-order DFT; reorder=0: DFT of the bit-reversed input.
