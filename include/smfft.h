@@ -130,7 +130,7 @@ int smfft_pipeline_release(void);
  * device from then on; smfft_select_report() lists the decisions, "select_reset" forgets them), "twiddle" (0 = table+powers
  * [default], 1 = MUFU __sincosf), "quirk_4096" (1 = reproduce FFT_4096_inverse_noreorder running
  * the forward transform, CT/SM_FFT_parameters.cuh:388; default 0 = mathematically correct),
- * "ctas_per_sm" (0 = built-in), "pipeline_chunk_mib" (default chunk of smfft_pipeline_host, 1..1024, default 128), "two_pass_chunk_mib" (batch chunk = scratch size of the multi-pass transforms, 2^15 points and up, 1..65536, default 1024), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
+ * "ctas_per_sm" (0 = built-in), "pipeline_chunk_mib" (default chunk of smfft_pipeline_host, 1..1024, default 128), "multi_pass_chunk_mib" (alias "two_pass_chunk_mib"; batch chunk = scratch size of the multi-pass transforms, 2^15 points and up, 1..65536, default 1024), "carveout" (experiment: -2 = per kernel [default], -1 = driver default, 0..100 = percent
  * of shared memory), "device_sms" (read-only). */
 int smfft_set_option(const char* key, int value);
 int smfft_get_option(const char* key);

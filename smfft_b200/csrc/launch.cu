@@ -489,7 +489,11 @@ int smfft_set_option(const char* key, int value)
     if (!strcmp(key, "twiddle")) { if (value < 0 || value > 1) return fail("twiddle must be 0 or 1"); g_opt_tw = value; return 0; }
     if (!strcmp(key, "quirk_4096")) { g_opt_quirk4096 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
-    if (!strcmp(key, "two_pass_chunk_mib")) { if (value < 1 || value > 65536) return fail("two_pass_chunk_mib must be 1..65536"); g_big_chunk_mib = value; return 0; }
+    if (!strcmp(key, "two_pass_chunk_mib") || !strcmp(key, "multi_pass_chunk_mib")) {  // two names, one option: the passes became three from 2^21 points
+        if (value < 1 || value > 65536) return fail("multi_pass_chunk_mib must be 1..65536");
+        g_big_chunk_mib = value;
+        return 0;
+    }
     if (!strcmp(key, "pipeline_chunk_mib")) { if (value < 1 || value > 1024) return fail("pipeline_chunk_mib must be 1..1024"); g_pipe_chunk_bytes = value << 20; return 0; }
     if (!strcmp(key, "carveout")) {  // experiment switch: takes effect for kernels not launched yet (or after a new process)
         if (value < -2 || value > 100) return fail("carveout must be -2 (per kernel), -1 (driver default) or 0..100");
@@ -514,7 +518,7 @@ int smfft_get_option(const char* key)
     if (!strcmp(key, "quirk_4096")) return g_opt_quirk4096;
     if (!strcmp(key, "ctas_per_sm")) return g_opt_ctas_per_sm;
     if (!strcmp(key, "carveout")) return g_opt_carveout;
-    if (!strcmp(key, "two_pass_chunk_mib")) return g_big_chunk_mib;
+    if (!strcmp(key, "two_pass_chunk_mib") || !strcmp(key, "multi_pass_chunk_mib")) return g_big_chunk_mib;
     if (!strcmp(key, "pipeline_chunk_mib")) return g_pipe_chunk_bytes >> 20;
     if (!strcmp(key, "device_sms")) { DeviceState* ds = nullptr; return get_device_state(&ds) ? -1 : ds->sms; }
     return -1;

@@ -54,6 +54,8 @@ def test_argument_errors_do_not_need_a_device(lib):
     assert lib.smfft_set_option(b"no_such_option", 1) != 0
     assert lib.smfft_set_option(b"twiddle", 1) == 0 and lib.smfft_get_option(b"twiddle") == 1
     assert lib.smfft_set_option(b"twiddle", 0) == 0
+    assert lib.smfft_set_option(b"multi_pass_chunk_mib", 64) == 0 and lib.smfft_get_option(b"two_pass_chunk_mib") == 64   # one option, two names
+    assert lib.smfft_set_option(b"two_pass_chunk_mib", 1024) == 0 and lib.smfft_set_option(b"multi_pass_chunk_mib", 0) != 0
 
 
 def test_no_cpu_fallback(lib):
