@@ -425,7 +425,7 @@ def other_modes(x, y, reps=5):
                     cu.cufftDestroy(h)
             out["c2c_two_pass"][str(nbig)] = r
         real_points = 2 * BATCH_POINTS          # the same 4 GiB read as floats
-        for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
+        for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384):
             nf = real_points // n
             out["r2c"][str(n)] = row(med(lambda: sm.R2C_C2R_external_benchmark(x, y, n, nf, 0)), real_points * 8)
             out["c2r"][str(n)] = row(med(lambda: sm.R2C_C2R_external_benchmark(x, y, n, nf, 1)), real_points * 8)

@@ -81,7 +81,7 @@ int smfft_stockham_external_benchmark(const void* d_in, void* d_out, int fft_siz
 int smfft_stockham_multiple_benchmark(const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse,
                                       double* ms);
 
-/* ---- Stockham R2C / C2R: real N = 64..8192 (the reference: 512..4096) ---------------------------
+/* ---- Stockham R2C / C2R: real N = 64..16384 (the reference: 512..4096; multiple: up to 8192) ----
  * replaces void FFT_external_benchmark(float*, float*, int FFT_size, int nFFTs, int inverse,
  *                                      double*)                                        RC:396-433
  *          void FFT_multiple_benchmark(float*, float*, int, int, double*)              RC:435-467

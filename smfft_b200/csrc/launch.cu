@@ -413,7 +413,7 @@ static int c2c_call(Call* c, const void* d_in, void* d_out, int fft_size, long l
 static int r2c_call(Call* c, const void* d_in, void* d_out, int fft_size, long long n_ffts, int inverse, int reps)
 {
     const int en = ilog2_exact(fft_size);
-    if (en < 6 || en > 13) return fail("smfft: wrong FFT length %d (R2C/C2R supports real 64..8192)", fft_size);
+    if (en < 6 || en > 14 || (en == 14 && reps > 1)) return fail("smfft: wrong FFT length %d (R2C/C2R supports real 64..16384, FFT_multiple up to 8192)", fft_size);
     if (n_ffts < 0) return fail("smfft: negative nFFTs");
     long long ffts = reps > 1 ? n_ffts / reps : n_ffts;
     *c = Call{inverse ? kernels::MODE_C2R : kernels::MODE_R2C, en - 1, inverse ? 1 : 0, 1, reps, d_in, d_out, ffts * (fft_size / 2)};

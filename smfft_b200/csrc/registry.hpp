@@ -185,7 +185,7 @@ EntryList build_entries_large()
 {
     using namespace kernels;
     struct Table {
-        KernelEntry tab[24];
+        KernelEntry tab[32];
         int n = 0;
     };
     static const Table table = [] {
@@ -193,6 +193,13 @@ EntryList build_entries_large()
         KernelEntry* tab = t.tab;
         int i = 0;
 #define SMFFT_ADD(...) tab[i++] = make_entry<E, __VA_ARGS__>()
+        // 16384 reals on the 8192-point core: R2C / C2R external, TMA and thread staging
+        if constexpr (E == 13) {
+            SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA, TW_LUT, 1);
+            SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA, TW_MUFU, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA, TW_MUFU, 1);
+            SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_LDG, TW_LUT, 1);
+            SMFFT_ADD(MODE_R2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_LDG, TW_MUFU, 1);
+        }
         // 16384 points, one 128 KB buffer: TMA in, results out from registers, the refill issued behind the final exchange
         if constexpr (Tuning<E>::STAGES == 1) {
             SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_LUT, 1);

@@ -185,6 +185,13 @@ struct TuningReal<12> {
     static constexpr int B = 4, TILE_E = 12, F = 1, STAGES = 2, MINB = 3, CTAS = 3, PF = 1;
     static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
 };
+// 16384 reals (beyond the reference): the 8192-point core, the shape of Tuning<13> -- R = 32 [32,32,8] (C2R: reversed [8,32,32]),
+// three 64 KB buffers, one CTA per SM; the mirrored real passes own their pairs (U = 4 butterflies per thread in the last pass)
+template <>
+struct TuningReal<13> {
+    static constexpr int B = 5, TILE_E = 13, F = 1, STAGES = 3, MINB = 1, CTAS = 1, PF = 1;
+    static constexpr int STG = 0, STG_R2C = 0, STG_C2R = 0;
+};
 
 // arithmetic flavour of one kernel instance (BlockCfg::DUAL_, bit flags): 0 = scalar, 1 = dual-lane, 2 = packed (re, im)
 // add / subtract in the butterflies, 4 = reversed pass plan.  Packed add / subtract removes ~9 % of the issue slots; it pays where a kernel is issue-bound
@@ -218,7 +225,7 @@ struct ArithFor {
     static constexpr int value = SMFFT_FORCE_ARITH;
 #else
     static constexpr int value = REPS > 1 ? ((MODE == 1 && (E == 9 || E == 10)) ? 0 : (MODE == 0 && E == 5 && SMFFT_XSHFL_MULTIPLE) ? 10 : 2)
-                                 : (MODE == 2 && (E == 11 || E == 12)) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
+                                 : (MODE == 2 && (E == 11 || E == 12 || E == 13)) ? 6  // + reversed plan: the C2R pass owns its pairs (MirrorC2R)
                                  : (MODE == 2 || (MODE == 1 && (E >= 11 || E == 5))) ? 2
                                  : (MODE == 0 && E == 14) ? SMFFT_T14_ARITH
                                  : (MODE == 0 && (E == 11 || E == 13 || (E == 12 && (REORDER == 0 || kNoR32E12)))) ? 2 : 0;  // C2C on R = 16 plans (and 8192 points), sustained load

@@ -96,6 +96,9 @@ int emu_run_late(const void* in, void* out, int variant, long long n_ffts, int g
         case 20: return run_cfg<12, 5, 1, 2, 1, 1, kernels::IO_TMA, TW_LUT, 2, 1, 1, 6>(i, o, n_ffts, grid, nullptr);
         case 21: return run_cfg<10, 4, 2, 2, 1, 1, kernels::IO_TMA_STG, TW_LUT, 2, 1, 1, 6>(i, o, n_ffts, grid, nullptr);
         case 22: return run_cfg<10, 4, 1, 0, 1, 1, kernels::IO_LDG, TW_MUFU, 1, 1, 0, 4>(i, o, n_ffts, grid, nullptr);
+        // 16384 reals: the 8192-point core [32,32,8] (three buffers) with the mirrored real passes -- R2C plain plan, C2R reversed [8,32,32]
+        case 23: return run_cfg<13, 5, 1, 1, 0, 1, kernels::IO_TMA, TW_LUT, 3, 1, 1, 2>(i, o, n_ffts, grid, nullptr);
+        case 24: return run_cfg<13, 5, 1, 2, 1, 1, kernels::IO_TMA, TW_LUT, 3, 1, 1, 6>(i, o, n_ffts, grid, nullptr);
     }
     return -1;
 }

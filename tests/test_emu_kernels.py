@@ -272,14 +272,16 @@ def test_8192_and_16384_point_c2c(emu, e, which):
                                             (10, 11, "c2r"), (11, 11, "c2r"), (12, 11, "c2r"),
                                             (13, 11, "c2c_fwd_r"), (14, 11, "c2c_inv_r"), (15, 7, "c2c_fwd_r"),
                                             (16, 12, "r2c"), (17, 9, "r2c"), (18, 10, "r2c"),
-                                            (19, 12, "c2c_fwd_r"), (20, 12, "c2r"), (21, 10, "c2r"), (22, 10, "c2c_inv_r")])
+                                            (19, 12, "c2c_fwd_r"), (20, 12, "c2r"), (21, 10, "c2r"), (22, 10, "c2c_inv_r"),
+                                            (23, 13, "r2c"), (24, 13, "c2r")])
 def test_late_prefetch_points(emu, variant, e, kind):
     """The next tile's load issued after a later pass (kernel parameter PF): one persistent CTA over many
     tiles; a refill that lands in a buffer still being read shows up as wrong data in the emulator.
     Variants 6-9: the register-direct input path (IO_REG, measured slower than TMA staging, kept as an experiment).
     Variants 10-15: the reversed pass plan (small radix first) and the mirrored C2R head that it enables.
     Variants 16-18 (and 8): mirrored R2C ownership with several butterfly pairs per thread.
-    Variants 19-22: reversed plans with a radix-4 first pass and the mirrored C2R head with 2 / 4 butterfly pairs."""
+    Variants 19-22: reversed plans with a radix-4 first pass and the mirrored C2R head with 2 / 4 butterfly pairs.
+    Variants 23-24: 16384 reals on the 8192-point core (three 64 KB buffers, two TMA boxes per tile), mirrored R2C / C2R."""
     n = 1 << e
     nf = max(7 * 4096 // n, 7) + 1
     if kind.startswith("c2c"):

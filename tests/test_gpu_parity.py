@@ -111,7 +111,7 @@ def test_quirk_4096_switch(sm):
     assert O.rel_l2(run_c2c(sm, x, True, False), O.ct_c2c_fp64(x, True, False)) < TOL
 
 
-@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
 @pytest.mark.parametrize("io", [0, 1, 2, 3])
 def test_r2c_c2r_vs_oracle(sm, n, io):
     sm.set_option("io", io)
@@ -748,7 +748,7 @@ def test_c2c_beyond_the_reference(sm, n, io, tw):
 def test_randomized_configurations(sm, seed):
     """Seeded sweep over what a caller can combine: size (32..4194304), batch count (odd, prime, one, many tiles per CTA), staging
     (io 0..5), twiddle source, direction, order, in place or not, first-use selection on or off -- C2C against the FP64 DFT, and
-    R2C / C2R (64..8192 reals) against the packed FP64 forms.  A mismatch names the configuration."""
+    R2C / C2R (64..16384 reals) against the packed FP64 forms.  A mismatch names the configuration."""
     rng = np.random.default_rng(seed)
     try:
         for it in range(60):
@@ -774,7 +774,7 @@ def test_randomized_configurations(sm, seed):
             if not in_place:
                 assert np.array_equal(c64(dx), x), cfg            # the input is left alone
         for it in range(30):
-            n = 1 << int(rng.integers(6, 14))                      # real length
+            n = 1 << int(rng.integers(6, 15))                      # real length, 64 .. 16384
             nf = min(int(rng.choice([1, 3, 17, 149, 257, 1031])), (1 << 22) // n)
             io, tw = int(rng.integers(0, 5)), int(rng.integers(0, 2))
             cfg = dict(real_n=n, nf=nf, io=io, tw=tw)

@@ -70,6 +70,14 @@ for n in (32, 1024, 4096):
     y = torch.empty_like(x)
     sm.exec_repeated(x, y, n, nf, False, True, 0, 3)
     sm.exec_repeated(x, y, n, nf, False, False, 0, 3)
+# 16384 reals (8192-point core, R2C and C2R) with more tiles than SMs
+xr = O.uniform_f32(2 * 148 + 3, 16384)
+dr = torch.from_numpy(xr).cuda()
+dc = torch.zeros((xr.shape[0], 8192, 2), dtype=torch.float32, device="cuda")
+sm.exec_r2c_c2r(dr, dc, 16384, xr.shape[0], 0)
+sm.exec_r2c_c2r(dc, dr, 16384, xr.shape[0], 1)
+torch.cuda.synchronize()
+bad += O.rel_l2(dr.cpu().numpy() / 8192, xr) > 1e-5
 # 8192 / 16384 points with more tiles than SMs: every persistent CTA refills its buffers (16384: the ONE buffer, behind the
 # final exchange, while the results leave from registers)
 for n, nf in ((8192, 3 * 148 + 7), (16384, 2 * 148 + 9)):
