@@ -129,18 +129,17 @@ EntryList build_entries()
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_LUT, 1);
         SMFFT_ADD(MODE_C2C, 0, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_LDG, TW_MUFU, 1);
         SMFFT_ADD(MODE_C2C, 1, 1, IO_LDG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_LDG, TW_MUFU, 1);
-        // register-output staging (TMA in, STG out), C2C and C2R
-        {
-            SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_LUT, 1);
-            SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_LUT, 1);
-            SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_MUFU, 1);
-            SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_MUFU, 1);
-            if constexpr (ShapeFor<E, MODE_C2R, 1, 1>::type::STAGES >= 2) {
-                SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_MUFU, 1);
-            }
-            if constexpr (ShapeFor<E, MODE_R2C, 1, 1>::type::STAGES >= 2) {
-                SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_MUFU, 1);
-            }
+        // register-output staging (TMA in, STG out): C2C always (one-stage shapes refill behind the final exchange), the real
+        // transforms where the shape has two tile buffers
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_LUT, 1);
+        SMFFT_ADD(MODE_C2C, 0, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 0, 0, IO_TMA_STG, TW_MUFU, 1);
+        SMFFT_ADD(MODE_C2C, 1, 1, IO_TMA_STG, TW_MUFU, 1); SMFFT_ADD(MODE_C2C, 1, 0, IO_TMA_STG, TW_MUFU, 1);
+        if constexpr (ShapeFor<E, MODE_C2R, 1, 1>::type::STAGES >= 2) {
+            SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_C2R, 1, 1, IO_TMA_STG, TW_MUFU, 1);
+        }
+        if constexpr (ShapeFor<E, MODE_R2C, 1, 1>::type::STAGES >= 2) {
+            SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_LUT, 1); SMFFT_ADD(MODE_R2C, 0, 1, IO_TMA_STG, TW_MUFU, 1);
         }
         // register-direct input (IO_REG): 1024-point natural-order C2C -- R = 32, one warp per transform, two transforms per
         // 64-thread CTA, one CTA per tile, launched with the driver's default L1 carve-out (tuning.hpp, RegDirect)
